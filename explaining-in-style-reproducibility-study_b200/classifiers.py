@@ -1,0 +1,129 @@
+"""Classifier wrappers with the reference's interface (stay PyTorch, same CUDA stream).
+
+Mirrors ``ResNet`` (reference ``stylex/resnet_classifier.py:30-71``) and ``MobileNet``
+(``stylex/mobilenet_classifier.py:29-73``): same constructor arguments, same attributes, same
+``classify_images(images) -> logits[B,2]`` semantics (resize / interpolate, optional ImageNet
+normalisation, raw logits out).  Differences, all forced by the environment:
+
+* no ``torch.hub.load`` (there is no network): the architecture comes from the installed
+  torchvision; pass ``model=`` to hand in an already-built module (synthetic configs do).
+* the hot path only ever feeds tensors, so the PIL branch of ``classify_images`` is kept but
+  is not on the measured path.
+
+BASELINE north_star: "The classifier forward (ResNet-18/MobileNetV2) runs through PyTorch in
+the same stream" -- nothing here calls the native library.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+_MEAN = (0.485, 0.456, 0.406)
+_STD = (0.229, 0.224, 0.225)
+
+
+def _device(cuda_rank: int) -> torch.device:
+    return torch.device(f"cuda:{cuda_rank}") if torch.cuda.is_available() else torch.device("cpu")
+
+
+class _Wrapper:
+    kind = ""
+
+    def _finish(self, model: nn.Module, image_size: int, normalize: bool):
+        from torchvision.transforms import transforms
+
+        self.model = model
+        self.image_size = image_size
+        self.normalize = normalize
+        self.tensor_transform = transforms.Compose([transforms.Normalize(mean=list(_MEAN), std=list(_STD))])
+        for p in self.model.parameters():
+            p.requires_grad = False
+        self.model.eval()
+
+    def to(self, device):
+        self.model.to(device)
+        return self
+
+    def preprocess(self, images: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def classify_images(self, images) -> torch.Tensor:
+        return self.model(self.preprocess(images))
+
+    __call__ = classify_images
+
+
+class ResNet(_Wrapper):
+    """ResNet-18 with a 2-way head; tensors are resized to 224x224 (resnet_classifier.py:56-71)."""
+
+    kind = "resnet"
+
+    def __init__(self, model_name: Optional[str] = None, cuda_rank: int = 0, output_size: int = 2, image_size: int = 32,
+                 normalize: bool = True, model: Optional[nn.Module] = None):
+        from torchvision.transforms import transforms
+
+        if model is None:
+            import torchvision
+
+            model = torchvision.models.resnet18(weights=None)
+            model.fc = nn.Linear(512, output_size)
+            if model_name is not None:
+                model.load_state_dict(torch.load(os.path.join("trained_classifiers", model_name), map_location="cpu"))
+            model = model.to(_device(cuda_rank))
+        self.resnet_dim = 224
+        self.image_transform = transforms.Compose([transforms.Resize(self.resnet_dim), transforms.ToTensor()])
+        self._finish(model, image_size, normalize)
+
+    def preprocess(self, images):
+        from torchvision.transforms.functional import resize
+
+        if isinstance(images, torch.Tensor):
+            x = resize(images, [self.resnet_dim, self.resnet_dim])       # resnet_classifier.py:60-61
+        else:
+            x = self.image_transform(images)
+        if self.normalize:
+            x = self.tensor_transform(x)                                 # resnet_classifier.py:67-68
+        return x
+
+
+class MobileNet(_Wrapper):
+    """MobileNetV2 with a 2-way head; tensors are interpolated to image_size (mobilenet_classifier.py:57-73)."""
+
+    kind = "mobilenet"
+
+    def __init__(self, model_name: Optional[str] = None, cuda_rank: int = 0, output_size: int = 2, image_size: int = 32,
+                 normalize: bool = True, model: Optional[nn.Module] = None):
+        from torchvision.transforms import transforms
+
+        if model is None:
+            import torchvision
+
+            model = torchvision.models.mobilenet_v2(weights=None)
+            model.classifier[1] = nn.Linear(1280, output_size)
+            if model_name is not None:
+                model.load_state_dict(torch.load(os.path.join("trained_classifiers", model_name), map_location="cpu"))
+            model = model.to(_device(cuda_rank))
+        self.mobilenet_dim = 224
+        self.image_transform = transforms.Compose([transforms.ToTensor()])
+        self._finish(model, image_size, normalize)
+
+    def preprocess(self, images):
+        if isinstance(images, torch.Tensor):
+            x = F.interpolate(images, size=self.image_size)              # mobilenet_classifier.py:62
+        else:
+            x = F.interpolate(self.image_transform(images), size=self.image_size)
+        if self.normalize:
+            x = self.tensor_transform(x)                                 # mobilenet_classifier.py:69-70
+        return x
+
+
+def make_classifier(kind: str, model: nn.Module, image_size: int):
+    if kind == "resnet":
+        return ResNet(model=model, image_size=image_size)
+    if kind == "mobilenet":
+        return MobileNet(model=model, image_size=image_size)
+    raise ValueError(kind)

@@ -1,0 +1,95 @@
+"""The oracle (oracle/stylex_oracle.py) against the committed golden vectors that were produced by
+running the UNMODIFIED reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import stylex_b200
+from stylex_b200 import synthetic, classifiers
+from oracle import stylex_oracle as O
+from helpers import state_from_npz, tiny_cnn_from
+
+torch.set_grad_enabled(False)
+
+
+def test_generator_small_matches_reference(golden):
+    z = golden("gen_small.npz")
+    sd = state_from_npz(z, "G.")
+    w = torch.from_numpy(z["latents"])
+    noise = torch.from_numpy(z["noise"])
+    L = len(O.generator_layout(sd))
+    img, sc = O.generator_forward(sd, O.styles_def_to_tensor([(w, L)]), noise, get_style_coords=True)
+    # same torch ops in the same order as the reference: tolerance only covers CPU-kernel differences
+    assert np.abs(img.numpy() - z["image"]).max() <= 2e-6
+    assert np.abs(sc.numpy() - z["style_coords"]).max() <= 2e-6
+    img2, sc2 = O.generator_forward(sd, torch.from_numpy(z["styles_per_layer"]), noise, get_style_coords=True)
+    assert np.abs(img2.numpy() - z["image_per_layer"]).max() <= 2e-6
+    assert np.abs(sc2.numpy() - z["style_coords_per_layer"]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("size", [64, 256])
+def test_generator_full_shapes_match_reference(golden, size):
+    z = golden("gen_full.npz")
+    sd = synthetic.make_generator_state(size, seed=42)
+    n = z[f"image_{size}"].shape[0]
+    w = synthetic.make_latents(n, 42)
+    noise = synthetic.make_noise(size, 42)
+    fp = np.array([float(sd["blocks.0.conv1.weight"].double().sum()),
+                   float(sd[f"blocks.{len(O.generator_layout(sd)) - 1}.conv2.weight"].double().abs().sum()),
+                   float(w.double().sum()), float(noise.double().sum())])
+    assert np.allclose(fp, z[f"fp_{size}"], rtol=1e-9, atol=1e-6), "torch CPU RNG drifted: seeded inputs differ"
+    L = len(O.generator_layout(sd))
+    img, sc = O.generator_forward(sd, O.styles_def_to_tensor([(w, L)]), noise, get_style_coords=True)
+    assert np.abs(img.numpy() - z[f"image_{size}"]).max() <= 5e-6
+    assert np.abs(sc.numpy() - z[f"style_coords_{size}"]).max() <= 5e-6
+    assert sc.shape[1] == {64: 2464, 256: 4512}[size]
+
+
+@pytest.mark.parametrize("kind", ["mobilenet", "resnet"])
+def test_attfind_sweep_matches_verbatim_notebook(golden, kind):
+    z = golden("attfind_small.npz")
+    sd = state_from_npz(z, "G.")
+    model = tiny_cnn_from(z, f"{kind}.clf.")
+    clf = classifiers.make_classifier(kind, model, int(z["image_size"]))
+    latents = torch.from_numpy(z[f"{kind}.latents"])
+    noise = torch.from_numpy(z["noise"])
+    res = O.attfind_sweep(sd, clf.classify_images, latents, noise, shift_size=1.0)
+    assert np.abs(res["style_coordinates"].numpy() - z[f"{kind}.style_coordinates"]).max() <= 2e-6
+    assert np.abs(res["base_prob"].numpy() - z[f"{kind}.base_prob"]).max() <= 1e-5
+    assert np.abs(res["minima"].numpy() - z[f"{kind}.minima"][0]).max() <= 2e-6
+    assert np.abs(res["maxima"].numpy() - z[f"{kind}.maxima"][0]).max() <= 2e-6
+    # the notebook patches biases in place (quirk Q2: fp32 residue accumulates); the oracle is drift-free
+    err = np.abs(res["style_change"].numpy() - z[f"{kind}.style_change"]).max()
+    assert err <= 2e-5, err
+    picks, merged, _ = O.attfind_select(res["style_change"].numpy(), res["base_prob"].numpy(), 5, 0.5)
+    assert [tuple(p) for p in z[f"{kind}.picks0"]] == picks[0]
+    assert [tuple(p) for p in z[f"{kind}.picks1"]] == picks[1]
+    assert [tuple(p) for p in z[f"{kind}.merged"]] == merged
+
+
+def test_selection_golden_picks_from_golden_effects(golden):
+    """selection alone, on the reference's own effects (no float noise in between): must be exact."""
+    z = golden("attfind_small.npz")
+    for kind in ("mobilenet", "resnet"):
+        picks, merged, _ = O.attfind_select(z[f"{kind}.style_change"], z[f"{kind}.base_prob"], 5, 0.5)
+        assert [tuple(p) for p in z[f"{kind}.picks0"]] == picks[0]
+        assert [tuple(p) for p in z[f"{kind}.picks1"]] == picks[1]
+        assert [tuple(p) for p in z[f"{kind}.merged"]] == merged
+
+
+def test_find_significant_styles_cases(golden):
+    z = golden("select_cases.npz")
+    for name in z["cases"]:
+        eff = z[f"{name}.effects"]
+        mie, k = z[f"{name}.params"]
+        for c in (0, 1):
+            got = O.find_significant_styles(eff.copy(), int(k), c, max_image_effect=float(mie))
+            assert got == [tuple(p) for p in z[f"{name}.picks{c}"]], (name, c)
+
+
+def test_sindex_mapping():
+    pairs = synthetic.generator_pairs(64)
+    assert O.sindex_to_block_idx_and_index(pairs, 0) == (0, 0)
+    assert O.sindex_to_block_idx_and_index(pairs, 1023) == (0, 1023)
+    assert O.sindex_to_block_idx_and_index(pairs, 1024) == (1, 0)
+    assert O.sindex_to_block_idx_and_index(pairs, 2463) == (4, 95)
