@@ -1,6 +1,16 @@
 """B200-native AttFind hot path of StylEx (drop-in for the reference's Python surface).
 
-See DESIGN.md.  Host-side mirror of the reference interface lives in ``modules`` / ``attfind`` /
-``classifiers``; the CUDA kernels and the C-ABI library are under ``csrc`` (``include/stylex_b200.h``).
+See DESIGN.md.  Host-side mirror of the reference interface: ``modules`` (Generator, GeneratorBlock,
+RGBBlock, Conv2DMod, Blur), ``attfind`` (attfind_extraction, find_significant_styles, ...), ``classifiers``
+(ResNet / MobileNet wrappers, PyTorch), ``dist`` (latent sharding + the one all-gather).  The CUDA kernels and
+the C-ABI library live under ``csrc`` (declared in ``include/stylex_b200.h``, bound in ``_native``).
 """
 from . import synthetic  # noqa: F401
+from . import _native  # noqa: F401
+from .modules import (Blur, Conv2DMod, Generator, GeneratorBlock, GeneratorPlan, RGBBlock, image_noise,  # noqa: F401
+                      styles_def_to_tensor)
+from .classifiers import MobileNet, ResNet, make_classifier  # noqa: F401
+from .attfind import (attfind_extraction, attfind_select, attfind_sweep, find_significant_styles,  # noqa: F401
+                      get_min_max_style_vectors, sindex_to_block_idx_and_index)
+
+__version__ = "0.1.0"

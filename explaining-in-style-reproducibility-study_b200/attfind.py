@@ -1,0 +1,334 @@
+"""AttFind: the StyleSpace perturbation sweep and the greedy top-k selection.
+
+Host-side mirror of the reference notebook ``stylex/run_attfind_combined.ipynb`` (NB; raw JSON line
+numbers): ``attfind_extraction`` NB:269-417, ``sindex_to_block_idx_and_index`` NB:220-234,
+``get_min_max_style_vectors`` NB:237-252, ``find_significant_styles`` NB:731-758, the class split and
+merged ranking of cells 14/16 (NB:695-714, NB:775-814).  Same names, argument meaning and outputs.
+
+What changed underneath:
+
+* no per-shift Python loop and no ``bias += shift`` patching of the model (quirk Q2): for every conv of
+  the generator, all (coordinate, direction) pairs that perturb that conv's style vector are one batch;
+  ``sx_attfind_make_styles`` writes the shifted style rows, ``sx_generator_forward(start_conv=c)`` re-runs
+  only the suffix of the network from that conv on, reusing the latent's clean prefix;
+* the classifier stays PyTorch on the same stream (BASELINE north_star); ``sx_attfind_scatter_effects``
+  stores the logit deltas; ``sx_attfind_select`` does the class split + greedy selection on device with
+  numpy-exact float64 column means;
+* latents are sharded across ranks; one all-gather of the effects at the end (``dist.py``).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .modules import Generator, styles_def_to_tensor
+
+_sel_ws = N.Workspace()
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers with the notebook's names
+# ---------------------------------------------------------------------------------------------
+def sindex_to_block_idx_and_index(generator, sindex):
+    """NB:220-234."""
+    tmp_idx = sindex
+    for idx, block in enumerate(generator.blocks):
+        if tmp_idx < block.num_style_coords:
+            return idx, tmp_idx
+        tmp_idx = tmp_idx - block.num_style_coords
+    return None, None
+
+
+def get_min_max_style_vectors(style_coordinates: torch.Tensor):
+    """NB:237-252: elementwise min / max over the image axis (native kernel)."""
+    if style_coordinates is None or style_coordinates.shape[0] == 0:
+        raise ValueError('No images pass the threshold check')
+    N.require_cuda(style_coordinates)
+    N.device_check()
+    sc = N.f32c(style_coordinates)
+    n, s = sc.shape
+    mn = torch.empty(s, device=sc.device, dtype=torch.float32)
+    mx = torch.empty_like(mn)
+    N.check(N.lib().sx_attfind_minmax(sc.data_ptr(), n, s, s, mn.data_ptr(), mx.data_ptr(), N.stream_ptr()), "sx_attfind_minmax")
+    return mn, mx
+
+
+def discriminator_filter(discriminator, generated_image, threshold, probabilities=None):
+    """NB:255-266 (PyTorch discriminator; not on the hot path)."""
+    if probabilities is not None:
+        output_generated = discriminator(generated_image, probabilities=probabilities)
+    else:
+        output_generated = discriminator(generated_image)
+    if threshold is None:
+        return output_generated
+    if output_generated < threshold:
+        return (False, output_generated)
+    return (True, output_generated)
+
+
+# ---------------------------------------------------------------------------------------------
+# the sweep
+# ---------------------------------------------------------------------------------------------
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous latent shard of `rank`; remainder spread over the first ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@torch.no_grad()
+def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.Tensor, shift_size: float = 1.0,
+                  precision: Optional[str] = None, max_batch: int = 128, rank: int = 0, world_size: int = 1,
+                  sindices: Optional[Sequence[int]] = None, image_indices: Optional[Sequence[int]] = None,
+                  gather: bool = True, stats: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """Phases A(second half)-C of ``attfind_extraction`` (NB:316-389) for latents ``[N, latent]``.
+
+    Every rank computes the style coordinates, base images and base logits of ALL N latents (cheap, and it
+    makes minima/maxima identical everywhere without a collective), then sweeps its own contiguous shard of
+    latents over all S coordinates x 2 directions.  Returns the notebook's datasets as device tensors:
+    'style_change' [N,2,S,2] (after the all-gather when ``gather``; the local shard otherwise), 'base_prob'
+    [N,2] (raw logits, quirk Q3), 'style_coordinates' [N,S], 'minima' / 'maxima' [S], 'latents'.
+
+    ``sindices`` / ``image_indices`` restrict the sweep to a subset (bounded benchmark / test samples);
+    untouched entries of 'style_change' stay 0.
+    """
+    precision = precision or G.precision
+    N.require_cuda(latents, noise)
+    N.device_check()
+    lib = N.lib()
+    plan = G.plan()
+    dev = latents.device
+    L = G.num_layers
+    S, row = plan.S, plan.row
+    n_all = latents.shape[0]
+    max_batch = max(2, max_batch - (max_batch % 2))
+    half = max_batch // 2
+    plan.reserve(max_batch, precision)
+    stream = N.stream_ptr()
+
+    lat = N.f32c(latents)
+    styles_all = plan.styles(styles_def_to_tensor([(lat, L)]).contiguous())           # [N, row]
+    base_logits = torch.empty(n_all, 2, device=dev, dtype=torch.float32)
+    for i in range(0, n_all, max_batch):                                                # NB:316-334, batched
+        rgb = plan.forward(styles_all[i: i + max_batch].contiguous(), noise, precision=precision)
+        base_logits[i: i + max_batch] = classifier.classify_images(rgb).float()
+    minima = torch.empty(S, device=dev, dtype=torch.float32)
+    maxima = torch.empty_like(minima)
+    N.check(lib.sx_attfind_minmax(styles_all.data_ptr(), n_all, S, row, minima.data_ptr(), maxima.data_ptr(), stream),
+            "sx_attfind_minmax")                                                        # NB:340
+
+    lo, hi = shard_range(n_all, rank, world_size)
+    mine = list(range(lo, hi))
+    if image_indices is not None:
+        keep = set(int(i) for i in image_indices)
+        mine = [i for i in mine if i in keep]
+    effects = torch.zeros(hi - lo, 2, S, 2, device=dev, dtype=torch.float32)
+    # coordinate runs per conv: [(conv index, first sindex, count)] -- contiguous runs of the requested sindices
+    runs = _coord_runs(plan.conv_coords, sindices, half)
+    styles_b = torch.empty(max_batch, row, device=dev, dtype=torch.float32)
+    rgb_b = torch.empty(max_batch, 3, G.image_size, G.image_size, device=dev, dtype=torch.float32)
+    evals = 0
+    for n in mine:                                                                      # NB:346
+        base_row = styles_all[n]
+        plan.forward(styles_all[n: n + 1], noise, save_cache=True, precision=precision, out=rgb_b[:1])
+        for conv, first, cnt in runs:                                                   # NB:356-387, batched per conv
+            b = 2 * cnt
+            N.check(lib.sx_attfind_make_styles(base_row.data_ptr(), minima.data_ptr(), maxima.data_ptr(), styles_b.data_ptr(),
+                                               row, first, cnt, float(shift_size), stream), "sx_attfind_make_styles")
+            rgb = plan.forward(styles_b[:b], noise, start_conv=conv, precision=precision, out=rgb_b[:b])
+            logits = classifier.classify_images(rgb).float().contiguous()               # NB:384 (raw rgb, quirk Q4)
+            N.check(lib.sx_attfind_scatter_effects(logits.data_ptr(), base_logits[n].data_ptr(), effects[n - lo].data_ptr(),
+                                                   0, S, first, cnt, stream), "sx_attfind_scatter_effects")
+            evals += b
+    if stats is not None:
+        stats["coord_evals"] = stats.get("coord_evals", 0) + evals
+    if gather and world_size > 1:
+        from .dist import gather_effects
+        effects = gather_effects(effects, n_all, world_size)
+    return {"style_change": effects, "latents": lat, "base_prob": base_logits, "minima": minima, "maxima": maxima,
+            "style_coordinates": styles_all[:, :S].contiguous()}
+
+
+def _coord_runs(conv_coords, sindices, half) -> List[Tuple[int, int, int]]:
+    runs = []
+    if sindices is None:
+        for conv, (off, width) in enumerate(conv_coords):
+            for s0 in range(0, width, half):
+                runs.append((conv, off + s0, min(half, width - s0)))
+        return runs
+    want = sorted(set(int(s) for s in sindices))
+    for conv, (off, width) in enumerate(conv_coords):
+        sel = [s for s in want if off <= s < off + width]
+        i = 0
+        while i < len(sel):
+            j = i
+            while j + 1 < len(sel) and sel[j + 1] == sel[j] + 1 and (j + 1 - i) < half:
+                j += 1
+            runs.append((conv, sel[i], j - i + 1))
+            i = j + 1
+    return runs
+
+
+# ---------------------------------------------------------------------------------------------
+# selection
+# ---------------------------------------------------------------------------------------------
+def _native_select(effects: torch.Tensor, base_logits: Optional[torch.Tensor], k: int, max_image_effect: float,
+                   class_index: int) -> List[Tuple[int, int]]:
+    N.require_cuda(effects, base_logits)
+    N.device_check()
+    lib = N.lib()
+    if effects.dtype not in (torch.float32, torch.float64):
+        effects = effects.float()
+    effects = effects.contiguous()
+    n, two, S, two2 = effects.shape
+    assert two == 2 and two2 == 2, "effects must be [N, 2, S, 2]"
+    if n == 0:
+        # the notebook dies here too (quirk Q7: "arrays used as indices must be of integer (or boolean) type")
+        raise IndexError(f"AttFind selection: class {class_index} has no images")
+    bl = None if base_logits is None else N.f32c(base_logits)
+    ws = _sel_ws.get(lib.sx_attfind_select_workspace_bytes(n, S), effects.device)
+    picks = torch.empty(2 * k, device=effects.device, dtype=torch.int32)
+    N.check(lib.sx_attfind_select(effects.data_ptr(), 1 if effects.dtype == torch.float64 else 0, N.ptr(bl), n, S, k,
+                                  float(max_image_effect), class_index, picks.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  N.stream_ptr()), "sx_attfind_select")
+    p = picks.cpu().tolist()
+    return [(p[2 * i], p[2 * i + 1]) for i in range(k)]
+
+
+def find_significant_styles(style_change_effect, num_indices, class_index, generator=None, classifier=None,
+                            all_dlatents=None, style_min=None, style_max=None, max_image_effect=0.2, label_size=2,
+                            sindex_offset=0, device=None):
+    """NB:731-758, same signature.  ``style_change_effect`` is the per-class array [N_c, 2, S, 2] (numpy or
+    tensor; the notebook passes a float64 copy).  Unlike the notebook the input is NOT modified in place."""
+    if isinstance(style_change_effect, np.ndarray):
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        eff = torch.from_numpy(np.ascontiguousarray(style_change_effect)).to(dev)
+    else:
+        eff = style_change_effect
+    picks = _native_select(eff, None, int(num_indices), float(max_image_effect), int(class_index))
+    return [(d, s + sindex_offset) for d, s in picks]
+
+
+def attfind_select(style_change_effect: torch.Tensor, base_probs: torch.Tensor, num_indices: int = 5,
+                   effect_threshold: float = 0.5):
+    """Cells 14 + 16 (NB:695-714, NB:775-814): per-class greedy picks on device, merged ranking on the host.
+
+    Returns (picks {0: [(direction, sindex)], 1: [...]}, merged [(direction, sindex)], scores).  The merged
+    ranking evaluates the notebook's own numpy expression on the <= 2k picked columns only.
+    """
+    labels = torch.argmax(base_probs, dim=1)
+    for c in (0, 1):
+        if int((labels == c).sum()) == 0:
+            raise IndexError(f"AttFind selection: class {c} has no images (the notebook fails here too, quirk Q7)")
+    picks = {c: _native_select(style_change_effect, base_probs, num_indices, effect_threshold * 5, c) for c in (0, 1)}
+    s0 = [s for _, s in picks[0]]
+    joined = [(1 - d, s) for d, s in picks[1] if s not in s0]                            # NB:802
+    joined += picks[0]                                                                   # NB:803
+    scores = []
+    for d, s in joined:                                                                  # NB:806-809
+        od = 1 if d == 0 else 0
+        col_a = style_change_effect[:, d, s, 0].float().cpu().numpy()
+        col_b = style_change_effect[:, od, s, 1].float().cpu().numpy()
+        scores.append(np.mean(col_a) + np.mean(col_b))
+    order = np.argsort(scores)[::-1]                                                     # NB:811
+    return picks, [joined[i] for i in order], [float(scores[i]) for i in order]
+
+
+# ---------------------------------------------------------------------------------------------
+# the notebook's entry point
+# ---------------------------------------------------------------------------------------------
+DATASET_NAMES = ("style_change", "latents", "base_prob", "minima", "maxima", "style_coordinates", "original_images",
+                 "noise", "discriminator")
+
+
+@torch.no_grad()
+def attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, dataset_name, noise, num_style_coords,
+                       shift_size, discriminator_threshold, image_size=64, batch_size=1, cuda_rank=0,
+                       use_discriminator=False, use_old_architecture=True, precision=None, max_batch=128,
+                       rank=0, world_size=1):
+    """``attfind_extraction`` of NB:269-417 with the same arguments (extra keyword arguments have defaults).
+
+    Phase A (encode each image, classify it, build ``concat_w``, optional discriminator filter; NB:300-336)
+    runs the PyTorch encoder / classifier / discriminator exactly like the notebook; phases B-C are
+    ``attfind_sweep``.  Writes ``style_change_records.hdf5`` with the 9 datasets of NB:395-403 when h5py is
+    importable, else ``style_change_records.npz`` with the same names; also returns them as a dict.
+    """
+    if batch_size != 1:
+        raise ValueError('Please use a batch_size equal to 1')                          # NB:284-285
+    dev = torch.device("cuda", cuda_rank)
+    G = stylex.G
+    if num_style_coords != G.num_style_coords:
+        raise ValueError(f"num_style_coords={num_style_coords} but the generator has {G.num_style_coords} (quirk Q5)")
+    latent_dim = G.latent_dim
+    image_latents = torch.zeros((num_images, latent_dim), device=dev)
+    original_images = torch.zeros((num_images, 3, image_size, image_size), device=dev)
+    discriminator_results = torch.zeros((num_images, 1), device=dev)
+    images_found = 0
+    for batch in iter(dataloader):                                                       # NB:300
+        if images_found >= num_images:
+            break
+        batch = batch.to(dev)
+        encoder_output = stylex.encoder(batch).unsqueeze(0)                              # NB:306
+        real_classified_logits = classifier.classify_images(batch)                       # NB:307
+        if use_old_architecture:
+            concat_w_tensor = torch.cat((encoder_output, real_classified_logits), dim=1)  # NB:312
+        else:
+            concat_w_tensor = torch.cat((encoder_output, torch.softmax(real_classified_logits, dim=1)), dim=1)
+        skip, discriminator_output = None, torch.zeros(1, device=dev)
+        if use_discriminator or getattr(stylex, "D", None) is not None:
+            w_latent_tensor = styles_def_to_tensor([(concat_w_tensor, G.num_layers)])
+            generated_image = G(w_latent_tensor, noise)
+            if use_old_architecture:
+                skip, discriminator_output = discriminator_filter(stylex.D, generated_image, discriminator_threshold)
+            else:
+                skip, discriminator_output = discriminator_filter(
+                    stylex.D, generated_image, discriminator_threshold,
+                    probabilities=torch.softmax(classifier.classify_images(generated_image), dim=1))
+        if use_discriminator and skip:
+            continue
+        original_images[images_found] = batch
+        image_latents[images_found] = concat_w_tensor
+        discriminator_results[images_found] = discriminator_output
+        images_found += 1
+    if images_found == 0:
+        raise ValueError('No images pass the threshold check')
+    res = attfind_sweep(G, classifier, image_latents[:images_found], noise, shift_size=shift_size, precision=precision,
+                        max_batch=max_batch, rank=rank, world_size=world_size)
+    out = {
+        "style_change": _pad(res["style_change"], num_images), "latents": image_latents,
+        "base_prob": _pad(res["base_prob"], num_images), "minima": res["minima"][None], "maxima": res["maxima"][None],
+        "style_coordinates": _pad(res["style_coordinates"], num_images), "original_images": original_images,
+        "noise": noise.reshape(1, image_size, image_size, 1), "discriminator": discriminator_results,
+    }
+    if rank == 0 and results_folder is not None:
+        save_records(results_folder, out)
+    return out
+
+
+def _pad(t: torch.Tensor, n: int) -> torch.Tensor:
+    if t.shape[0] == n:
+        return t
+    out = torch.zeros((n,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+    out[: t.shape[0]] = t
+    return out
+
+
+def save_records(results_folder: str, datasets: Dict[str, torch.Tensor]) -> str:
+    """NB:394-417: the 9 float32 datasets of ``style_change_records.hdf5`` (npz when h5py is absent)."""
+    arrays = {k: datasets[k].detach().float().cpu().numpy() for k in DATASET_NAMES}
+    os.makedirs(results_folder, exist_ok=True)
+    try:
+        import h5py
+    except ImportError:
+        path = os.path.join(results_folder, "style_change_records.npz")
+        np.savez(path, **arrays)
+        return path
+    path = os.path.join(results_folder, "style_change_records.hdf5")
+    with h5py.File(path, "w") as f:
+        for k, v in arrays.items():
+            f.create_dataset(k, v.shape, dtype="f")[:] = v
+    return path

@@ -1,0 +1,425 @@
+// bandwidth.cuh -- the HBM-bound kernels of the generator: modulate, bilinear 2x upsample, ToRGB
+// (+ fused upsample/blur of the previous rgb), noise/leaky-ReLU, layout changes, and the small
+// per-batch tables (style affine, demodulation coefficients).  All loads/stores are 16-byte vectors on
+// the contiguous (channel for NHWC, x for NCHW) axis; grids are sized in multiples of the SM count.
+#pragma once
+
+#include "common.cuh"
+
+namespace sx {
+
+// =================================================================================================
+// NHWC plan kernels (T = float | __nv_bfloat16)
+// =================================================================================================
+
+// out[b, p, c] = in[b|0, p, c] * (style[b, c] + 1)          (style may be null: plain broadcast copy)
+template <typename T>
+__global__ void __launch_bounds__(256) modulate_kernel(const T* __restrict__ in, long long in_bstride,
+                                                       const float* __restrict__ style, int style_stride,
+                                                       T* __restrict__ out, int B, long long P, int C) {
+  constexpr int V = Elem<T>::kVec;
+  using vec_t = typename Elem<T>::vec_t;
+  const int cv = C / V;
+  const long long per_b = P * cv;
+  const long long total = (long long)B * per_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long r = i - (long long)b * per_b;
+    const int c = (int)(r % cv) * V;
+    vec_t v = *reinterpret_cast<const vec_t*>(in + (long long)b * in_bstride + r * V);
+    if (style) {
+      float f[V];
+      unpack(v, f);
+      const float* s = style + (long long)b * style_stride + c;
+#pragma unroll
+      for (int j = 0; j < V; ++j) f[j] *= __ldg(s + j) + 1.f;
+      pack(f, v);
+    }
+    *reinterpret_cast<vec_t*>(out + i * V) = v;
+  }
+}
+
+template <typename T>
+int launch_modulate(const T* in, long long in_bstride, const float* style, int style_stride, T* out, int B,
+                    long long P, int C, cudaStream_t st) {
+  SX_REQUIRE(C % Elem<T>::kVec == 0, "modulate: C=%d not a multiple of %d", C, Elem<T>::kVec);
+  const long long total = (long long)B * P * (C / Elem<T>::kVec);
+  if (total == 0) return SX_OK;
+  modulate_kernel<T><<<ew_grid(total, 256), 256, 0, st>>>(in, in_bstride, style, style_stride, out, B, P, C);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+// torch's upsample_bilinear2d(align_corners=False, scale 2) source index computation
+__device__ __forceinline__ void bilinear_src(int o, int n_in, int& i0, int& i1, float& l0, float& l1) {
+  float src = (o + 0.5f) * 0.5f - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = src - i0;
+  l0 = 1.f - l1;
+}
+
+// out[b, 2H, 2W, C] = upsample2x(in[b|0]) * (style[b, c] + 1)      (ST:679,693-694 fused with the
+// activation-side modulation of the next conv1).  H, W are the INPUT sizes.
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_modulate_kernel(const T* __restrict__ in, long long in_bstride,
+                                                                  const float* __restrict__ style, int style_stride,
+                                                                  T* __restrict__ out, int B, int H, int W, int C) {
+  constexpr int V = Elem<T>::kVec;
+  using vec_t = typename Elem<T>::vec_t;
+  const int cv = C / V;
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)B * OH * OW * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * V;
+    long long r = i / cv;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bilinear_src(oy, H, y0, y1, ly0, ly1);
+    bilinear_src(ox, W, x0, x1, lx0, lx1);
+    const T* src = in + (long long)b * in_bstride + c;
+    float f00[V], f01[V], f10[V], f11[V], o[V];
+    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y0 * W + x0) * C), f00);
+    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y0 * W + x1) * C), f01);
+    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y1 * W + x0) * C), f10);
+    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y1 * W + x1) * C), f11);
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[j] = ly0 * (lx0 * f00[j] + lx1 * f01[j]) + ly1 * (lx0 * f10[j] + lx1 * f11[j]);
+    if (style) {
+      const float* s = style + (long long)b * style_stride + c;
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] *= __ldg(s + j) + 1.f;
+    }
+    vec_t v;
+    pack(o, v);
+    *reinterpret_cast<vec_t*>(out + i * V) = v;
+  }
+}
+
+template <typename T>
+int launch_upsample2x_modulate(const T* in, long long in_bstride, const float* style, int style_stride, T* out, int B,
+                               int H, int W, int C, cudaStream_t st) {
+  SX_REQUIRE(C % Elem<T>::kVec == 0, "upsample: C=%d not a multiple of %d", C, Elem<T>::kVec);
+  const long long total = (long long)B * 4 * H * W * (C / Elem<T>::kVec);
+  if (total == 0) return SX_OK;
+  upsample2x_modulate_kernel<T><<<ew_grid(total, 256), 256, 0, st>>>(in, in_bstride, style, style_stride, out, B, H, W, C);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+// value of blur3x3_reflect(upsample2x(p + q)) at (y, x) of the (2h x 2w) image; p, q: fp32 planes [h, w] (q may be null).
+__device__ __forceinline__ float ld2(const float* __restrict__ p, const float* __restrict__ q, int i) {
+  float v = __ldg(p + i);
+  if (q) v += __ldg(q + i);
+  return v;
+}
+__device__ __forceinline__ float up2(const float* __restrict__ p, const float* __restrict__ q, int h, int w, int y, int x) {
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilinear_src(y, h, y0, y1, ly0, ly1);
+  bilinear_src(x, w, x0, x1, lx0, lx1);
+  return ly0 * (lx0 * ld2(p, q, y0 * w + x0) + lx1 * ld2(p, q, y0 * w + x1)) +
+         ly1 * (lx0 * ld2(p, q, y1 * w + x0) + lx1 * ld2(p, q, y1 * w + x1));
+}
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+__device__ __forceinline__ float up2_blur(const float* __restrict__ p, const float* __restrict__ q, int h, int w, int y, int x) {
+  const int H = 2 * h, W = 2 * w;
+  float acc = 0.f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = reflect1(y + dy, H);
+    const float ky = dy == 0 ? 2.f : 1.f;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = reflect1(x + dx, W);
+      const float kx = dx == 0 ? 2.f : 1.f;
+      acc += (ky * kx * (1.f / 16.f)) * up2(p, q, h, w, yy, xx);
+    }
+  }
+  return acc;
+}
+
+// RGBBlock (ST:618-629) for one block, fused with the previous block's Upsample+Blur tail:
+//   rgb[b, c, y, x] = sum_o y2[b, y, x, o] * (sr[b, o] + 1) * Wrgb[c, o]  +  blur(up2x(prev[b|0]))[c, y, x]
+// y2 NHWC (T), prev [Bp, 3, H/2, W/2] fp32 planar (null for the first block), rgb [B,3,H,W] fp32 planar.
+// One thread per pixel; the 3 x Co modulated weights of the sample sit in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) torgb_kernel(const T* __restrict__ y2, const float* __restrict__ rgb_style,
+                                                    int style_stride, const float* __restrict__ wrgb,
+                                                    const float* __restrict__ prev, long long prev_bstride,
+                                                    float* __restrict__ rgb, int H, int W, int Co) {
+  extern __shared__ float s_w[];  // [3][Co]
+  constexpr int V = Elem<T>::kVec;
+  using vec_t = typename Elem<T>::vec_t;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * Co; i += blockDim.x) {
+    const int o = i % Co;
+    s_w[i] = (__ldg(rgb_style + (long long)b * style_stride + o) + 1.f) * __ldg(wrgb + i);
+  }
+  __syncthreads();
+  const int HW = H * W;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    const T* src = y2 + ((long long)b * HW + pix) * Co;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int o = 0; o < Co; o += V) {
+      float f[V];
+      unpack(*reinterpret_cast<const vec_t*>(src + o), f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        a0 = fmaf(f[j], s_w[o + j], a0);
+        a1 = fmaf(f[j], s_w[Co + o + j], a1);
+        a2 = fmaf(f[j], s_w[2 * Co + o + j], a2);
+      }
+    }
+    const int y = pix / W, x = pix - y * W;
+    if (prev) {
+      const float* pp = prev + (long long)b * prev_bstride;
+      const int h = H / 2, w = W / 2;
+      a0 += up2_blur(pp, nullptr, h, w, y, x);
+      a1 += up2_blur(pp + h * w, nullptr, h, w, y, x);
+      a2 += up2_blur(pp + 2 * h * w, nullptr, h, w, y, x);
+    }
+    float* dst = rgb + (long long)b * 3 * HW + pix;
+    dst[0] = a0;
+    dst[HW] = a1;
+    dst[2 * HW] = a2;
+  }
+}
+
+template <typename T>
+int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const float* wrgb, const float* prev,
+                 long long prev_bstride, float* rgb, int B, int H, int W, int Co, cudaStream_t st) {
+  SX_REQUIRE(Co % Elem<T>::kVec == 0, "torgb: Co=%d not a multiple of %d", Co, Elem<T>::kVec);
+  if (B == 0) return SX_OK;
+  const int HW = H * W;
+  const int threads = HW >= 256 ? 256 : 64;
+  int gx = (HW + threads - 1) / threads;
+  dim3 grid(gx, B);
+  torgb_kernel<T><<<grid, threads, 3 * Co * sizeof(float), st>>>(y2, rgb_style, style_stride, wrgb, prev, prev_bstride,
+                                                              rgb, H, W, Co);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+// =================================================================================================
+// per-batch tables
+// =================================================================================================
+
+// K5: styles[b, j] = bias[j] + sum_k w[b, layer(j), k] * A[j, k]   (one warp per output, shuffle reduction)
+__global__ void __launch_bounds__(256) styles_affine_kernel(const float* __restrict__ w, const float* __restrict__ A,
+                                                            const float* __restrict__ bias,
+                                                            const int* __restrict__ col_layer, float* __restrict__ out,
+                                                            int B, int L, int latent, int row) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long t = warp; t < (long long)B * row; t += nwarps) {
+    const int b = (int)(t / row), j = (int)(t - (long long)b * row);
+    const float* wv = w + ((long long)b * L + __ldg(col_layer + j)) * latent;
+    const float* a = A + (long long)j * latent;
+    float acc = 0.f;
+    for (int k = lane; k < latent; k += 32) acc = fmaf(__ldg(wv + k), __ldg(a + k), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[t] = acc + __ldg(bias + j);
+  }
+}
+
+// demodulation coefficients of every conv from `first_conv` on, for the whole batch:
+//   d[b, doff_c + o] = rsqrt( sum_i (style[b, soff_c + i] + 1)^2 * wsq_c[i][o] + eps )      (ST:654-656)
+struct DemodConv {
+  const float* wsq;  // [Ci][Co]
+  int ci, co, soff, doff;
+};
+struct DemodParams {
+  DemodConv conv[2 * SX_MAX_BLOCKS];
+  int first_conv, num_convs;
+  const float* styles;
+  int style_stride;
+  float* dcoef;
+  int dcoef_stride;
+  float eps;
+};
+__global__ void __launch_bounds__(128) demod_kernel(DemodParams p) {
+  const DemodConv cv = p.conv[p.first_conv + blockIdx.z];
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  extern __shared__ float s_s2[];  // (style+1)^2 of this sample for this conv
+  const float* s = p.styles + (long long)b * p.style_stride + cv.soff;
+  for (int i = threadIdx.x; i < cv.ci; i += blockDim.x) {
+    const float t = __ldg(s + i) + 1.f;
+    s_s2[i] = t * t;
+  }
+  __syncthreads();
+  if (o >= cv.co) return;
+  float acc = 0.f;
+  for (int i = 0; i < cv.ci; ++i) acc = fmaf(s_s2[i], __ldg(cv.wsq + (long long)i * cv.co + o), acc);
+  p.dcoef[(long long)b * p.dcoef_stride + cv.doff + o] = rsqrtf(acc + p.eps);
+}
+
+// =================================================================================================
+// weight packing (sx_generator_load) -- one-off
+// =================================================================================================
+// W[Co][Ci][k][k] fp32  ->  wpk[tap][Ci][Co] fp32,  wbf[Co][tap*Ci + ci] bf16 (K-major),  wsq[Ci][Co] = sum_tap W^2
+__global__ void pack_weights_kernel(const float* __restrict__ W, float* __restrict__ wpk, __nv_bfloat16* __restrict__ wbf,
+                                    float* __restrict__ wsq, int Co, int Ci, int taps) {
+  const long long total = (long long)Co * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i / Ci), c = (int)(i - (long long)o * Ci);
+    float sq = 0.f;
+    for (int t = 0; t < taps; ++t) {
+      const float v = W[i * taps + t];
+      sq = fmaf(v, v, sq);
+      if (wpk) wpk[((long long)t * Ci + c) * Co + o] = v;
+      if (wbf) wbf[(long long)o * taps * Ci + (long long)t * Ci + c] = __float2bfloat16_rn(v);
+    }
+    if (wsq) wsq[(long long)c * Co + o] = sq;
+  }
+}
+
+// x0[y][x][o] = bias[o] + sum_{i,dy,dx} W[o][i][dy][dx] * blk[i][y+dy-1][x+dx-1]   (4x4, zero padded; ST:802,806)
+__global__ void initial_conv_kernel(const float* __restrict__ blk, const float* __restrict__ W, const float* __restrict__ bias,
+                                    float* __restrict__ x0, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 16 * C) return;
+  const int o = idx % C, pix = idx / C, y = pix / 4, x = pix % 4;
+  float acc = 0.f;
+  for (int i = 0; i < C; ++i)
+    for (int dy = 0; dy < 3; ++dy)
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        if (yy < 0 || yy > 3 || xx < 0 || xx > 3) continue;
+        acc = fmaf(W[(((long long)o * C + i) * 3 + dy) * 3 + dx], blk[(i * 4 + yy) * 4 + xx], acc);
+      }
+  x0[idx] = acc + bias[o];
+}
+
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(in[i]);
+}
+
+// =================================================================================================
+// reference-layout (NCHW fp32) ops behind the nn.Module forwards
+// =================================================================================================
+
+// x[B,C,H,W] fp32 * (style[b,c]+1)  ->  NHWC T   (32x32 shared-memory transpose, coalesced both ways)
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_modulate_kernel(const float* __restrict__ x, const float* __restrict__ style,
+                                                                    T* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      v = x[((long long)b * C + c) * HW + p];
+      if (style) v *= __ldg(style + (long long)b * C + c) + 1.f;
+    }
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, c = c0 + tx;
+    if (c < C && p < HW) out[((long long)b * HW + p) * C + c] = from_f<T>(tile[tx][j]);
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_nchw_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                              long long planes, int H, int W) {
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = planes * OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW);
+    const long long r = i / OW;
+    const int oy = (int)(r % OH);
+    const long long pl = r / OH;
+    out[i] = up2(x + pl * H * W, nullptr, H, W, oy, ox);
+  }
+}
+
+__global__ void __launch_bounds__(256) blur_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, long long planes,
+                                                        int H, int W) {
+  const long long total = planes * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    const long long r = i / W;
+    const int yy = (int)(r % H);
+    const float* p = x + (r / H) * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y2 = reflect1(yy + dy, H);
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x2 = reflect1(xx + dx, W);
+        acc += ((dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f)) * __ldg(p + y2 * W + x2);
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) noise_lrelu_nchw_kernel(const float* __restrict__ x, const float* __restrict__ inoise,
+                                                               const float* __restrict__ nw, const float* __restrict__ nb,
+                                                               float* __restrict__ out, int B, int C, int H, int W,
+                                                               int noise_batch, int S) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    long long r = i / W;
+    const int yy = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const float nz = __ldg(inoise + (long long)(noise_batch == 1 ? 0 : b) * S * S + (long long)xx * S + yy);
+    out[i] = lrelu02(x[i] + (nz * __ldg(nw + c) + __ldg(nb + c)));
+  }
+}
+
+// RGBBlock tail (ST:623-627): out = rgb + prev                       (no upsample)
+__global__ void __launch_bounds__(256) rgb_tail_nchw_kernel(const float* __restrict__ rgb, const float* __restrict__ prev,
+                                                            float* __restrict__ sum, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    sum[i] = rgb[i] + (prev ? prev[i] : 0.f);
+}
+//                            out = blur(upsample2x(rgb + prev))         (fused, [planes,h,w] -> [planes,2h,2w])
+__global__ void __launch_bounds__(256) rgb_tail_up_blur_nchw_kernel(const float* __restrict__ rgb, const float* __restrict__ prev,
+                                                                    float* __restrict__ out, long long planes, int h, int w) {
+  const int H = 2 * h, W = 2 * w;
+  const long long total = planes * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    const long long r = i / W;
+    const int yy = (int)(r % H);
+    const long long off = (r / H) * h * w;
+    out[i] = up2_blur(rgb + off, prev ? prev + off : nullptr, h, w, yy, xx);
+  }
+}
+
+// nn.Linear: one warp per output element
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+                                                     const float* __restrict__ bias, float* __restrict__ out, int B, int in_f,
+                                                     int out_f) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long t = warp; t < (long long)B * out_f; t += nwarps) {
+    const int b = (int)(t / out_f), j = (int)(t - (long long)b * out_f);
+    float acc = 0.f;
+    for (int k = lane; k < in_f; k += 32) acc = fmaf(__ldg(x + (long long)b * in_f + k), __ldg(Wt + (long long)j * in_f + k), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[t] = acc + (bias ? __ldg(bias + j) : 0.f);
+  }
+}
+
+}  // namespace sx

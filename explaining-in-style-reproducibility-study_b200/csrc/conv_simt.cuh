@@ -1,0 +1,196 @@
+// conv_simt.cuh -- fp32 implicit-GEMM convolution on the CUDA cores (FFMA), NHWC activations.
+//
+// This is the SX_PREC_FP32 path: the <=1e-4 parity mode of the modulated convolution (tcgen05 has no
+// fp32 MMA), the kernel behind the generic Conv2DMod op for shapes the tensor-core kernel does not
+// take (k=1, tiny channel counts), and the cross-check of the tcgen05 kernel (sx_tc_selftest).
+//
+// GEMM view (reference Conv2DMod.forward ST:647-667 with the modulation moved to the activations):
+//   M = B*H*W pixels, N = Co, K = k*k*Ci;  A[m, (tap,ci)] = xmod[b, y+dy, x+dx, ci] (zero padded),
+//   B[(tap,ci), o] = W[o, ci, tap]  (packed [tap][Ci][Co], shared by the whole batch).
+// Tile 64x64x16, 256 threads, 4x4 register micro-tile, double-buffered shared memory.
+#pragma once
+
+#include "common.cuh"
+
+namespace sx {
+
+constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 16, SIMT_THREADS = 256;
+
+struct ConvSimtParams {
+  const float* x;       // [Bx, H, W, Ci] NHWC, already modulated by (style+1)
+  long long x_bstride;  // elements between samples (0: one sample broadcast to the whole batch)
+  const float* wpk;     // [taps][Ci][Co]
+  int B, Ci, Co, H, W, KS;
+  ConvEpilogue ep;
+};
+
+__global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams p) {
+  __shared__ __align__(16) float As[2][SIMT_BK][SIMT_BM + 4];
+  __shared__ __align__(16) float Bs[2][SIMT_BK][SIMT_BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int HW = p.H * p.W;
+  const long long M = (long long)p.B * HW;
+  const long long m0 = (long long)blockIdx.x * SIMT_BM;
+  const int n0 = blockIdx.y * SIMT_BN;
+  const int pad = (p.KS - 1) / 2;
+  const int taps = p.KS * p.KS;
+  const int kchunks = (p.Ci + SIMT_BK - 1) / SIMT_BK;
+  const int iters = taps * kchunks;
+  const bool ci_vec = (p.Ci & 3) == 0;
+  const bool co_vec = (p.Co & 3) == 0;
+
+  // A loader: pixel a_pix of the tile, 4 channels starting at a_cg of the K chunk
+  const int a_pix = tid >> 2, a_cg = (tid & 3) * 4;
+  const long long a_m = m0 + a_pix;
+  const bool a_ok = a_m < M;
+  int a_b = 0, a_y = 0, a_x = 0;
+  if (a_ok) {
+    a_b = (int)(a_m / HW);
+    int r = (int)(a_m - (long long)a_b * HW);
+    a_y = r / p.W;
+    a_x = r - a_y * p.W;
+  }
+  const float* a_base = p.x + (long long)a_b * p.x_bstride;
+  // B loader: K row b_kr of the chunk, 4 output channels starting at b_ng
+  const int b_kr = tid >> 4, b_ng = (tid & 15) * 4;
+
+  float a_reg[4], b_reg[4];
+  auto load_tiles = [&](int it) {
+    const int tap = it / kchunks;
+    const int c0 = (it - tap * kchunks) * SIMT_BK;
+    const int dy = tap / p.KS - pad, dx = tap % p.KS - pad;
+    // ---- A
+    const int sy = a_y + dy, sx_ = a_x + dx;
+    const bool in = a_ok && sy >= 0 && sy < p.H && sx_ >= 0 && sx_ < p.W;
+    const int c = c0 + a_cg;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a_reg[j] = 0.f;
+    if (in) {
+      const float* src = a_base + ((long long)sy * p.W + sx_) * p.Ci + c;
+      if (ci_vec && c + 3 < p.Ci) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(src));
+        a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < p.Ci) a_reg[j] = __ldg(src + j);
+      }
+    }
+    // ---- B
+    const int kc = c0 + b_kr;
+    const int n = n0 + b_ng;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b_reg[j] = 0.f;
+    if (kc < p.Ci) {
+      const float* src = p.wpk + ((long long)tap * p.Ci + kc) * p.Co + n;
+      if (co_vec && n + 3 < p.Co) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(src));
+        b_reg[0] = v.x; b_reg[1] = v.y; b_reg[2] = v.z; b_reg[3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.Co) b_reg[j] = __ldg(src + j);
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[buf][a_cg + j][a_pix] = a_reg[j];
+    *reinterpret_cast<float4*>(&Bs[buf][b_kr][b_ng]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < iters) load_tiles(it + 1);
+#pragma unroll
+    for (int k = 0; k < SIMT_BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (it + 1 < iters) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue
+  const ConvEpilogue& ep = p.ep;
+  const int S = ep.noise_size;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int b = (int)(m / HW);
+    const int r = (int)(m - (long long)b * HW);
+    const int y = r / p.W, x = r - y * p.W;
+    float nz = 0.f;
+    if (ep.noise) nz = __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
+    float v[4], vr[4];
+    const int o0 = n0 + tx * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + j;
+      float t = acc[i][j];
+      if (o < p.Co) {
+        if (ep.dcoef) t *= __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + o);
+        if (ep.noise) t += nz * __ldg(ep.noise_w + o) + __ldg(ep.noise_b + o);
+        if (ep.act) t = lrelu02(t);
+      }
+      vr[j] = t;
+      if (o < p.Co && ep.next_style) t *= __ldg(ep.next_style + (long long)b * ep.next_style_stride + o) + 1.f;
+      v[j] = t;
+    }
+    if (ep.out_nchw_f32) {
+      float* out = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (o0 + j < p.Co) out[(((long long)b * p.Co + o0 + j) * p.H + y) * p.W + x] = v[j];
+    } else {
+      float* out = reinterpret_cast<float*>(ep.out) + m * p.Co + o0;
+      if (co_vec && o0 + 3 < p.Co) {
+        *reinterpret_cast<float4*>(out) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (o0 + j < p.Co) out[j] = v[j];
+      }
+    }
+    if (ep.out_raw) {
+      float* out = reinterpret_cast<float*>(ep.out_raw) + m * p.Co + o0;
+      if (co_vec && o0 + 3 < p.Co) {
+        *reinterpret_cast<float4*>(out) = make_float4(vr[0], vr[1], vr[2], vr[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (o0 + j < p.Co) out[j] = vr[j];
+      }
+    }
+  }
+}
+
+inline int launch_conv_simt(const ConvSimtParams& p, cudaStream_t stream) {
+  SX_REQUIRE(p.KS == 1 || p.KS == 3, "conv_simt: kernel size %d not supported (1 or 3)", p.KS);
+  const long long M = (long long)p.B * p.H * p.W;
+  if (M == 0 || p.Co == 0) return SX_OK;
+  dim3 grid((unsigned)((M + SIMT_BM - 1) / SIMT_BM), (unsigned)((p.Co + SIMT_BN - 1) / SIMT_BN));
+  conv_simt_kernel<<<grid, SIMT_THREADS, 0, stream>>>(p);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+}  // namespace sx

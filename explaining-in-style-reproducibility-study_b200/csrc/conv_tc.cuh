@@ -1,0 +1,408 @@
+// conv_tc.cuh -- bf16 implicit-GEMM 3x3 convolution on the 5th-gen tensor cores (sm_100a):
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma (kind::f16, fp32 accumulators in
+// TMEM) -> tcgen05.ld epilogue (demodulate, noise, leaky-ReLU, next-layer modulation) -> NHWC bf16 stores.
+//
+// GEMM view (Conv2DMod.forward ST:647-667 with the modulation moved onto the activations):
+//   D[m, o] = sum_{tap, ci} A[m, (tap, ci)] * Wk[o, (tap, ci)]
+//   m  = one output pixel; a CTA tile is 128 pixels = a (BB x BH x BW) box of the NHWC activation tensor
+//   A  = the same box shifted by the tap offset (dy, dx); TMA zero-fills out-of-bounds pixels, which IS the
+//        conv's zero padding -- no im2col buffer ever exists
+//   Wk = weights packed [Co][tap*Ci + ci] (K-major), shared by the whole batch (style lives in A / epilogue)
+// One K block = BLOCK_K channels of one tap.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..5 = epilogue (one TMEM lane quarter each).
+#pragma once
+
+#include "common.cuh"
+
+namespace sx {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr long long kWatchdogCycles = 4000000000LL;  // ~2 s: a dead barrier traps instead of hanging the box
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int which) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) {
+      printf("stylex_b200 conv_tc: barrier %d timed out (block %d,%d thread %d)\n", which, blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of BLOCK_K bf16
+// (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row groups SBO bytes apart, version 1 (Blackwell).
+template <int BLOCK_K>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t row_bytes = BLOCK_K * 2;
+  constexpr uint64_t sbo = 8 * row_bytes;                // bytes between 8-row core-matrix groups
+  constexpr uint64_t layout = row_bytes == 128 ? 2 : 4;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct ConvTcParams {
+  int B, H, W, Ci, Co, KS;
+  int BW, BH, BB;            // pixel box of one M tile: BB*BH*BW == 128
+  int tiles_x, tiles_y;      // W/BW, H/BH   (grid.x = tiles_b * tiles_y * tiles_x, grid.y = Co / BLOCK_N)
+  ConvEpilogue ep;
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+struct TcConfig {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;  // power of two >= 32
+  // dynamic smem: [1024 align slack][stages][barriers 256B][tables]
+  static size_t smem_bytes(int BB) {
+    return 1024 + (size_t)STAGES * kStageBytes + 256 + (size_t)(2 + 2 * BB) * BLOCK_N * sizeof(float);
+  }
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                              const __grid_constant__ CUtensorMap tmap_b,
+                                                              const ConvTcParams p) {
+  using Cfg = TcConfig<BLOCK_N, BLOCK_K, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_nw = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256);
+  float* s_nb = s_nw + BLOCK_N;
+  float* s_d = s_nb + BLOCK_N;            // [BB][BLOCK_N] demod coefficients
+  float* s_m = s_d + p.BB * BLOCK_N;      // [BB][BLOCK_N] next-layer (style+1)
+
+  const int warp_id = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tiles_per_b = p.tiles_x * p.tiles_y;
+  const int tb = blockIdx.x / tiles_per_b;
+  const int tr = blockIdx.x - tb * tiles_per_b;
+  const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+  const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int kc_per_tap = p.Ci / BLOCK_K;
+  const int num_kb = p.KS * p.KS * kc_per_tap;
+  const int pad = (p.KS - 1) / 2;
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  } else if (warp_id == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / kc_per_tap;
+        const int c0 = (kb - tap * kc_per_tap) * BLOCK_K;
+        const int dy = tap / p.KS - pad, dx = tap % p.KS - pad;
+        mbar_wait(&empty_bar[stage], phase ^ 1, 0);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0, x0 + dx, y0 + dy, b0);
+        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], tap * p.Ci + c0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp_id == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 1);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc<BLOCK_K>(smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t db = make_smem_desc<BLOCK_K>(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance the start address by k * 16 bf16 = 32 bytes inside the swizzled row (>>4 -> +2)
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const ConvEpilogue& ep = p.ep;
+    const int et = threadIdx.x - 64;  // 0..127
+    for (int i = et; i < BLOCK_N; i += 128) {
+      s_nw[i] = ep.noise ? __ldg(ep.noise_w + n0 + i) : 0.f;
+      s_nb[i] = ep.noise ? __ldg(ep.noise_b + n0 + i) : 0.f;
+    }
+    for (int i = et; i < p.BB * BLOCK_N; i += 128) {
+      const int bb = i / BLOCK_N, o = i - bb * BLOCK_N;
+      const int b = b0 + bb;
+      const bool ok = b < p.B;
+      s_d[i] = (ok && ep.dcoef) ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + o) : 1.f;
+      s_m[i] = (ok && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + o) + 1.f : 1.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+
+    const int q = warp_id & 3;          // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;        // tile row = TMEM lane
+    const int xx = r % p.BW;
+    const int yy = (r / p.BW) % p.BH;
+    const int bb = r / (p.BW * p.BH);
+    const int b = b0 + bb, y = y0 + yy, x = x0 + xx;
+    const bool valid = b < p.B;
+    float nz = 0.f;
+    if (valid && ep.noise) {
+      const int S = ep.noise_size;
+      nz = __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
+    }
+    const float* dd = s_d + bb * BLOCK_N;
+    const float* mm = s_m + bb * BLOCK_N;
+    const long long pix = ((long long)b * p.H + y) * p.W + x;
+
+    mbar_wait(tmem_full_bar, 0, 2);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      float f[32], fr[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]) * dd[c0 + j];
+        t += nz * s_nw[c0 + j] + s_nb[c0 + j];
+        if (ep.act) t = lrelu02(t);
+        fr[j] = t;
+        f[j] = t * mm[c0 + j];
+      }
+      if (valid) {
+        if (ep.out_nchw_f32) {
+          float* out = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
+        } else {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pack(f + j, pk);
+            *reinterpret_cast<uint4*>(out + j) = pk;
+          }
+        }
+        if (ep.out_raw) {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pack(fr + j, pk);
+            *reinterpret_cast<uint4*>(out + j) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+inline bool tc_shape_supported(int Ci, int Co, int H, int W, int KS) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  if (KS != 3) return false;
+  if (Ci % 32 != 0) return false;
+  if (!(Co == 32 || Co == 64 || Co == 128 || Co % 256 == 0)) return false;
+  if (H != W || !pow2(W) || W < 4) return false;
+  return true;
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+int launch_conv_tc_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvTcParams p, cudaStream_t stream) {
+  using Cfg = TcConfig<BLOCK_N, BLOCK_K, STAGES>;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(SX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const CUtensorMapSwizzle swz = BLOCK_K == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)p.Ci, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)p.W * p.Ci * 2, (cuuint64_t)p.H * p.W * p.Ci * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(A) failed: %d (B=%d H=%d W=%d Ci=%d)", (int)r, p.B, p.H, p.W, p.Ci);
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)p.KS * p.KS * p.Ci;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)p.Co};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wk), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d (Co=%d K=%llu)", (int)r, p.Co, (unsigned long long)ktot);
+  }
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, STAGES>;
+  const size_t smem = Cfg::smem_bytes(p.BB);
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tiles_b = (p.B + p.BB - 1) / p.BB;
+  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)(p.Co / BLOCK_N));
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, p);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+// x: NHWC bf16 [B,H,W,Ci] already modulated; wk: [Co][KS*KS*Ci] bf16.
+inline int launch_conv_tc(const __nv_bfloat16* x, const __nv_bfloat16* wk, int B, int Ci, int Co, int H, int W, int KS,
+                          const ConvEpilogue& ep, cudaStream_t stream) {
+  if (!tc_shape_supported(Ci, Co, H, W, KS))
+    return fail(SX_EUNSUPPORTED, "conv_tc: unsupported shape Ci=%d Co=%d H=%d W=%d k=%d (need k=3, Ci%%32==0, Co in {32,64,128,256n}, square pow2)",
+                Ci, Co, H, W, KS);
+  if (B == 0) return SX_OK;
+  ConvTcParams p;
+  p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KS = KS;
+  p.BW = W < BLOCK_M ? W : BLOCK_M;
+  p.BH = (BLOCK_M / p.BW) < H ? (BLOCK_M / p.BW) : H;
+  p.BB = BLOCK_M / (p.BW * p.BH);
+  p.tiles_x = W / p.BW;
+  p.tiles_y = H / p.BH;
+  p.ep = ep;
+  const int bn = Co % 256 == 0 ? 256 : Co;
+  const int bk = Ci % 64 == 0 ? 64 : 32;
+#define SX_TC_CASE(N, K, S) \
+  if (bn == N && bk == K) return launch_conv_tc_cfg<N, K, S>(x, wk, p, stream);
+  SX_TC_CASE(256, 64, 4)
+  SX_TC_CASE(128, 64, 6)
+  SX_TC_CASE(64, 64, 4)
+  SX_TC_CASE(32, 64, 5)
+  SX_TC_CASE(256, 32, 6)
+  SX_TC_CASE(128, 32, 6)
+  SX_TC_CASE(64, 32, 6)
+  SX_TC_CASE(32, 32, 6)
+#undef SX_TC_CASE
+  return fail(SX_EUNSUPPORTED, "conv_tc: no kernel for BLOCK_N=%d BLOCK_K=%d", bn, bk);
+}
+
+}  // namespace tc
+}  // namespace sx

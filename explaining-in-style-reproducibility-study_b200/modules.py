@@ -1,0 +1,395 @@
+"""Drop-in replacements for the reference's generator-side ``nn.Module`` classes.
+
+Same constructor arguments, attributes, forward signatures and **state-dict keys** as
+``stylex/stylex_train.py`` of the reference (``Blur`` :144-153, ``RGBBlock`` :604-629, ``Conv2DMod``
+:632-667, ``GeneratorBlock`` :670-718, ``Generator`` :747-840), so a reference checkpoint's
+``["StylEx"]["G.*"]`` entries load with ``load_state_dict``.  Every forward runs hand-written sm_100a
+kernels through the C ABI (``include/stylex_b200.h``); there is no PyTorch / CPU fallback.
+
+Two levels:
+
+* module level (``Conv2DMod.forward(x, y)``, ``GeneratorBlock.forward(x, prev_rgb, istyle, inoise)``,
+  ``RGBBlock.forward``, ``Blur.forward``): tensors cross the boundary in the reference's NCHW fp32
+  layout, one native op per reference op -- this is the compatibility surface.
+* plan level (``Generator.forward`` and the AttFind sweep): the whole synthesis network runs inside
+  the library on NHWC activations with fused epilogues (``GeneratorPlan``) -- this is the fast path.
+
+Inference only: the forwards do not record autograd graphs (the training step is a later row of
+SURVEY.md section 8f).
+"""
+from __future__ import annotations
+
+import ctypes
+from functools import partial
+from math import log2
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _native as N
+
+
+def exists(val):
+    return val is not None
+
+
+def leaky_relu(p=0.2):
+    return nn.LeakyReLU(p, inplace=True)
+
+
+def image_noise(n, im_size, device):
+    """reference stylex_train.py:336-337 (U[0,1) drawn on the CPU, then moved)."""
+    return torch.FloatTensor(n, im_size, im_size, 1).uniform_(0., 1.).to(_dev(device))
+
+
+def styles_def_to_tensor(styles_def):
+    """reference stylex_train.py:352-353."""
+    return torch.cat([t[:, None, :].expand(-1, n, -1) for t, n in styles_def], dim=1)
+
+
+def _dev(device):
+    return torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+
+
+def _prec(module) -> int:
+    return N.PRECISIONS[getattr(module, "precision", "fp32")]
+
+
+_op_ws = N.Workspace()
+
+
+def _noise_arg(inoise: torch.Tensor):
+    """[B|1, S, S, 1] (reference layout) -> dense fp32 [nb, S, S]."""
+    if inoise.dim() != 4 or inoise.shape[-1] != 1 or inoise.shape[1] != inoise.shape[2]:
+        raise ValueError(f"input_noise must be [B|1, S, S, 1], got {tuple(inoise.shape)}")
+    return N.f32c(inoise), inoise.shape[0], inoise.shape[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# L1 ops
+# ---------------------------------------------------------------------------------------------
+class Blur(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer('f', torch.Tensor([1, 2, 1]))
+
+    def forward(self, x):
+        N.require_cuda(x)
+        N.device_check()
+        x = N.f32c(x)
+        b, c, h, w = x.shape
+        out = torch.empty_like(x)
+        N.check(N.lib().sx_blur3x3_reflect(x.data_ptr(), out.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_blur3x3_reflect")
+        return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) on the native kernel."""
+    N.require_cuda(x)
+    N.device_check()
+    x = N.f32c(x)
+    b, c, h, w = x.shape
+    out = torch.empty(b, c, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
+    N.check(N.lib().sx_upsample2x_bilinear(x.data_ptr(), out.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_upsample2x_bilinear")
+    return out
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    N.require_cuda(x, weight, bias)
+    N.device_check()
+    x, weight = N.f32c(x), N.f32c(weight)
+    bias = None if bias is None else N.f32c(bias)
+    out = torch.empty(x.shape[0], weight.shape[0], device=x.device, dtype=torch.float32)
+    N.check(N.lib().sx_linear_fwd(x.data_ptr(), weight.data_ptr(), N.ptr(bias), out.data_ptr(), x.shape[0], x.shape[1],
+                                  weight.shape[0], N.stream_ptr()), "sx_linear_fwd")
+    return out
+
+
+def noise_lrelu(x: torch.Tensor, inoise: torch.Tensor, to_noise: nn.Linear) -> torch.Tensor:
+    """leaky_relu_0.2(x + to_noise(inoise[:, :H, :W]).permute(0,3,2,1)) -- reference :696-698,705."""
+    N.require_cuda(x, inoise)
+    N.device_check()
+    x = N.f32c(x)
+    nz, nb, ns = _noise_arg(inoise)
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    nw, nbias = N.f32c(to_noise.weight.detach()), N.f32c(to_noise.bias.detach())
+    N.check(N.lib().sx_noise_lrelu(x.data_ptr(), nz.data_ptr(), nw.data_ptr(), nbias.data_ptr(), out.data_ptr(), b, c, h, w,
+                                   nb, ns, N.stream_ptr()), "sx_noise_lrelu")
+    return out
+
+
+class Conv2DMod(nn.Module):
+    def __init__(self, in_chan, out_chan, kernel, demod=True, stride=1, dilation=1, eps=1e-8, **kwargs):
+        super().__init__()
+        self.filters = out_chan
+        self.demod = demod
+        self.kernel = kernel
+        self.stride = stride
+        self.dilation = dilation
+        self.weight = nn.Parameter(torch.randn((out_chan, in_chan, kernel, kernel)))
+        self.eps = eps
+        self.precision = kwargs.get("precision", "fp32")
+        nn.init.kaiming_normal_(self.weight, a=0, mode='fan_in', nonlinearity='leaky_relu')
+
+    def _get_same_padding(self, size, kernel, dilation, stride):
+        return ((size - 1) * (stride - 1) + dilation * (kernel - 1)) // 2
+
+    def forward(self, x, y):
+        if self.stride != 1 or self.dilation != 1:
+            raise NotImplementedError("stylex_b200 Conv2DMod: only stride=1, dilation=1 (all the reference ever uses)")
+        N.require_cuda(x, y, self.weight)
+        N.device_check()
+        x, y, w = N.f32c(x), N.f32c(y), N.f32c(self.weight.detach())
+        b, c, h, wd = x.shape
+        co, ci, k, _ = w.shape
+        if c != ci or y.shape != (b, ci):
+            raise ValueError(f"Conv2DMod: x {tuple(x.shape)} / style {tuple(y.shape)} do not match weight {tuple(w.shape)}")
+        prec = _prec(self)
+        lib = N.lib()
+        nbytes = lib.sx_conv2dmod_workspace_bytes(b, ci, co, h, wd, k, prec)
+        ws = _op_ws.get(nbytes, x.device)
+        out = torch.empty(b, co, h, wd, device=x.device, dtype=torch.float32)
+        N.check(lib.sx_conv2dmod_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), out.data_ptr(), b, ci, co, h, wd, k,
+                                     1 if self.demod else 0, float(self.eps), prec, ws.data_ptr(), ws.numel(),
+                                     N.stream_ptr()), "sx_conv2dmod_fwd")
+        return out
+
+
+class RGBBlock(nn.Module):
+    def __init__(self, latent_dim, input_channel, upsample, rgba=False):
+        super().__init__()
+        self.input_channel = input_channel
+        self.to_style = nn.Linear(latent_dim, input_channel)
+
+        out_filters = 3 if not rgba else 4
+        self.conv = Conv2DMod(input_channel, out_filters, 1, demod=False)
+
+        # kept as modules so the state-dict key `upsample.1.f` (the Blur buffer) exists like in the reference
+        self.upsample = nn.Sequential(
+            nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False),
+            Blur()
+        ) if upsample else None
+
+    def forward(self, x, prev_rgb, istyle):
+        b, c, h, w = x.shape
+        style = linear(istyle, self.to_style.weight.detach(), self.to_style.bias.detach())
+        x = self.conv(x, style)
+        prev = None if prev_rgb is None else N.f32c(prev_rgb)
+        up = exists(self.upsample)
+        out = torch.empty(b, x.shape[1], h * (2 if up else 1), w * (2 if up else 1), device=x.device, dtype=torch.float32)
+        N.check(N.lib().sx_rgb_add_upsample_blur(x.data_ptr(), N.ptr(prev), out.data_ptr(), b, x.shape[1], h, w,
+                                                 1 if up else 0, N.stream_ptr()), "sx_rgb_add_upsample_blur")
+        return out
+
+
+class GeneratorBlock(nn.Module):
+    def __init__(self, latent_dim, input_channels, filters, upsample=True, upsample_rgb=True, rgba=False):
+        super().__init__()
+
+        self.input_channels = input_channels
+        self.filters = filters
+
+        self.num_style_coords = self.input_channels + self.filters
+
+        self.upsample = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) if upsample else None
+
+        self.to_style1 = nn.Linear(latent_dim, input_channels)
+        self.to_noise1 = nn.Linear(1, filters)
+        self.conv1 = Conv2DMod(input_channels, filters, 3)
+
+        self.to_style2 = nn.Linear(latent_dim, filters)
+        self.to_noise2 = nn.Linear(1, filters)
+        self.conv2 = Conv2DMod(filters, filters, 3)
+
+        self.activation = leaky_relu()
+        self.to_rgb = RGBBlock(latent_dim, filters, upsample_rgb, rgba)
+
+    def forward(self, x, prev_rgb, istyle, inoise):
+        if exists(self.upsample):
+            x = upsample2x(x)
+        style1 = linear(istyle, self.to_style1.weight.detach(), self.to_style1.bias.detach())
+        x = self.conv1(x, style1)
+        x = noise_lrelu(x, inoise, self.to_noise1)
+        style2 = linear(istyle, self.to_style2.weight.detach(), self.to_style2.bias.detach())
+        style_coords = torch.cat([style1, style2], dim=-1)
+        x = self.conv2(x, style2)
+        x = noise_lrelu(x, inoise, self.to_noise2)
+        rgb = self.to_rgb(x, prev_rgb, istyle)
+        return x, rgb, style_coords
+
+
+# ---------------------------------------------------------------------------------------------
+# plan level
+# ---------------------------------------------------------------------------------------------
+class GeneratorPlan:
+    """Owns the native ``sx_generator_t`` of one ``Generator`` on one device (packed weights, workspaces)."""
+
+    def __init__(self, generator: "Generator"):
+        self.G = generator
+        self.handle = ctypes.c_void_p()
+        self.device = None
+        self._versions = None
+        self._ws = {}            # precision -> Workspace
+        self._cache_ok = {}      # precision -> bool (clean-prefix cache primed on the current workspace)
+        pairs = [(b.input_channels, b.filters) for b in generator.blocks]
+        self.pairs = pairs
+        ci = (ctypes.c_int * len(pairs))(*[p[0] for p in pairs])
+        co = (ctypes.c_int * len(pairs))(*[p[1] for p in pairs])
+        N.check(N.lib().sx_generator_create(ci, co, len(pairs), generator.latent_dim, ctypes.byref(self.handle)),
+                "sx_generator_create")
+        self.S = N.lib().sx_generator_num_style_coords(self.handle)
+        self.row = N.lib().sx_generator_style_row(self.handle)
+        # style-coordinate offset of every conv (2*block + {0,1}) and its width
+        self.conv_coords = []
+        off = 0
+        for cin, cout in pairs:
+            self.conv_coords.append((off, cin))
+            off += cin
+            self.conv_coords.append((off, cout))
+            off += cout
+
+    def __del__(self):
+        try:
+            if self.handle:
+                N.lib().sx_generator_destroy(self.handle)
+        except Exception:
+            pass
+
+    def _param_list(self):
+        G = self.G
+        ps = [G.initial_block, G.initial_conv.weight, G.initial_conv.bias]
+        for b in G.blocks:
+            ps += [b.to_style1.weight, b.to_style1.bias, b.to_noise1.weight, b.to_noise1.bias, b.conv1.weight,
+                   b.to_style2.weight, b.to_style2.bias, b.to_noise2.weight, b.to_noise2.bias, b.conv2.weight,
+                   b.to_rgb.to_style.weight, b.to_rgb.to_style.bias, b.to_rgb.conv.weight]
+        return ps
+
+    def sync(self):
+        """(re)pack the weights when the module's parameters changed (load_state_dict, .to(), optimiser step)."""
+        ps = self._param_list()
+        N.require_cuda(*ps)
+        versions = tuple((p.data_ptr(), p._version) for p in ps)
+        if versions == self._versions:
+            return
+        N.device_check()
+        dev = ps[0].device
+        keep = [N.f32c(p.detach()) for p in ps]
+        blocks = (N.sx_block_params * len(self.G.blocks))()
+        names = [f[0] for f in N.sx_block_params._fields_]
+        for i in range(len(self.G.blocks)):
+            for j, name in enumerate(names):
+                setattr(blocks[i], name, keep[3 + 13 * i + j].data_ptr())
+        with torch.cuda.device(dev):
+            N.check(N.lib().sx_generator_load(self.handle, keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(),
+                                              blocks, N.stream_ptr()), "sx_generator_load")
+        self.device = dev
+        self._versions = versions
+        self._cache_ok = {}
+
+    def reserve(self, max_batch: int, precision) -> None:
+        """size the workspace for ``max_batch`` up front (growing it later would drop the clean-prefix cache)."""
+        prec = N.PRECISIONS[precision]
+        self.sync()
+        need = N.lib().sx_generator_workspace_bytes(self.handle, max_batch, prec)
+        ws = self._ws.setdefault(prec, N.Workspace())
+        old = None if ws.buf is None else ws.buf.data_ptr()
+        buf = ws.get(need, self.device)
+        if buf.data_ptr() != old:
+            self._cache_ok[prec] = False
+
+    def styles(self, w: torch.Tensor) -> torch.Tensor:
+        """w [B, L, latent] -> styles [B, row] = [style coords (S) | ToRGB styles]."""
+        self.sync()
+        N.require_cuda(w)
+        w = N.f32c(w)
+        if w.dim() != 3 or w.shape[1] != len(self.pairs) or w.shape[2] != self.G.latent_dim:
+            raise ValueError(f"styles must be [B, {len(self.pairs)}, {self.G.latent_dim}], got {tuple(w.shape)}")
+        out = torch.empty(w.shape[0], self.row, device=w.device, dtype=torch.float32)
+        N.check(N.lib().sx_generator_styles(self.handle, w.data_ptr(), out.data_ptr(), w.shape[0], N.stream_ptr()),
+                "sx_generator_styles")
+        return out
+
+    def forward(self, styles_all: torch.Tensor, input_noise: torch.Tensor, start_conv: int = 0, save_cache: bool = False,
+                precision="fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        prec = N.PRECISIONS[precision]
+        self.sync()
+        N.require_cuda(styles_all, input_noise)
+        if styles_all.dtype != torch.float32 or not styles_all.is_contiguous() or styles_all.shape[1] != self.row:
+            raise ValueError(f"styles_all must be contiguous fp32 [B, {self.row}]")
+        B = styles_all.shape[0]
+        nz, nb, ns = _noise_arg(input_noise)
+        S = self.G.image_size
+        if ns != S:
+            raise ValueError(f"noise map is {ns}x{ns}, generator image_size is {S}")
+        self.reserve(B, prec)
+        if start_conv > 0 and not self._cache_ok.get(prec, False):
+            raise RuntimeError("AttFind suffix forward without a primed clean-prefix cache (call forward(save_cache=True) first)")
+        ws = self._ws[prec].buf
+        if out is None:
+            out = torch.empty(B, 3, S, S, device=styles_all.device, dtype=torch.float32)
+        N.check(N.lib().sx_generator_forward(self.handle, styles_all.data_ptr(), nz.data_ptr(), nb, out.data_ptr(), B,
+                                             start_conv, 1 if save_cache else 0, prec, ws.data_ptr(), ws.numel(),
+                                             N.stream_ptr()), "sx_generator_forward")
+        if save_cache:
+            self._cache_ok[prec] = True
+        return out
+
+
+class Generator(nn.Module):
+    def __init__(self, image_size, latent_dim, network_capacity=16, transparent=False, attn_layers=[], no_const=False,
+                 fmap_max=512):
+        super().__init__()
+        if transparent or attn_layers or no_const:
+            raise NotImplementedError("stylex_b200 Generator: transparent / attn_layers / no_const are default-off "
+                                      "extras of the reference that are outside the AttFind hot path (SURVEY.md section 2)")
+        self.image_size = image_size
+        self.latent_dim = latent_dim
+        self.num_layers = int(log2(image_size) - 1)
+        self.precision = "fp32"
+
+        filters = [network_capacity * (2 ** (i + 1)) for i in range(self.num_layers)][::-1]
+
+        set_fmap_max = partial(min, fmap_max)
+        filters = list(map(set_fmap_max, filters))
+        init_channels = filters[0]
+        filters = [init_channels, *filters]
+
+        in_out_pairs = zip(filters[:-1], filters[1:])
+        self.no_const = no_const
+
+        self.initial_block = nn.Parameter(torch.randn((1, init_channels, 4, 4)))
+        self.initial_conv = nn.Conv2d(filters[0], filters[0], 3, padding=1)
+        self.blocks = nn.ModuleList([])
+        self.attns = nn.ModuleList([])
+
+        for ind, (in_chan, out_chan) in enumerate(in_out_pairs):
+            not_first = ind != 0
+            not_last = ind != (self.num_layers - 1)
+            self.attns.append(None)
+            self.blocks.append(GeneratorBlock(latent_dim, in_chan, out_chan, upsample=not_first, upsample_rgb=not_last,
+                                              rgba=transparent))
+        self._plan = None
+
+    @property
+    def num_style_coords(self):
+        return sum(b.num_style_coords for b in self.blocks)
+
+    def plan(self) -> GeneratorPlan:
+        if self._plan is None:
+            object.__setattr__(self, "_plan", GeneratorPlan(self))
+        return self._plan
+
+    def forward(self, styles, input_noise, get_style_coords=False):
+        """styles [B, L, latent], input_noise [B|1, S, S, 1] -> rgb [B,3,S,S] (, style_coords [B, S_total])."""
+        plan = self.plan()
+        styles_all = plan.styles(styles)
+        rgb = plan.forward(styles_all, input_noise, precision=self.precision)
+        if get_style_coords:
+            return rgb, styles_all[:, :plan.S].clone()
+        return rgb
+
+    def forward_from_styles(self, styles_all, input_noise):
+        """StyleSpace entry point: styles_all [B, style_row] as returned by ``plan().styles``."""
+        return self.plan().forward(styles_all, input_noise, precision=self.precision)

@@ -1,0 +1,189 @@
+/*
+ * stylex_b200.h -- C ABI of libstylex_b200.so: the B200 (sm_100a) kernels under the reference's
+ * AttFind hot path.  Plain pointers and sizes only; no torch / ATen / pybind types.
+ *
+ * The reference (NoahVl/Explaining-In-Style-Reproducibility-Study, "R/") is pure Python and has no
+ * FFI of its own; its boundary is the Python class surface of R/stylex/stylex_train.py ("ST") and the
+ * AttFind notebook R/stylex/run_attfind_combined.ipynb ("NB", raw JSON line numbers).  Each entry
+ * point below names the reference interface it sits under.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch), unless it is
+ *     documented as host; the library never frees or keeps caller memory beyond the call, except
+ *     sx_generator_load(), which copies (packs) the weights into memory owned by the handle.
+ *   - all work is enqueued on `stream` (a cudaStream_t; pass torch.cuda.current_stream().cuda_stream)
+ *     and no entry point synchronises the device (sx_generator_load / sx_tc_selftest excepted).
+ *   - return value: SX_OK (0) or a negative SX_E* code; the message is in sx_last_error()
+ *     (thread local).  Nothing throws, nothing exits.  There is NO CPU fallback: a missing GPU, a
+ *     non-sm_100 device or an unsupported shape is an error.
+ *   - boundary tensors use the reference's layout (NCHW, fp32).  Inside the generator plan
+ *     activations are NHWC in fp32 (SX_PREC_FP32, CUDA-core FFMA, <=1e-4 parity mode) or bf16
+ *     (SX_PREC_BF16, tcgen05/TMEM/TMA implicit GEMM with fp32 accumulation).
+ */
+#ifndef STYLEX_B200_H
+#define STYLEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SX_VERSION 100
+
+#define SX_OK 0
+#define SX_EINVAL (-1)       /* bad argument */
+#define SX_ECUDA (-2)        /* CUDA runtime / driver error */
+#define SX_EUNSUPPORTED (-3) /* shape or device not supported by the sm_100a kernels */
+#define SX_ENOMEM (-4)       /* caller workspace too small */
+#define SX_ESTATE (-5)       /* handle not loaded / cache not primed */
+
+#define SX_PREC_FP32 0
+#define SX_PREC_BF16 1
+
+#define SX_MAX_BLOCKS 10
+
+typedef void* sx_stream_t;             /* cudaStream_t */
+typedef struct sx_generator sx_generator_t;
+
+int sx_version(void);
+const char* sx_last_error(void);
+/* 0 when the current device is a compute-capability 10.x GPU, SX_EUNSUPPORTED / SX_ECUDA otherwise. */
+int sx_device_check(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+unsigned long long sx_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * L1 ops in the reference's tensor layout (NCHW fp32).  These sit under the nn.Module forwards.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Conv2DMod.forward(x, y) -- ST:647-667.  x[B,Ci,H,W], weight[Co,Ci,k,k] (k = 1 or 3), style[B,Ci]
+ * -> out[B,Co,H,W].  out = d[b,o] * conv(W, x * (style+1)), d = rsqrt(sum((W*(style+1))^2) + eps) if
+ * demod else 1 ("same" zero padding, stride 1, dilation 1).  precision selects the FFMA fp32 kernel or
+ * the bf16 tcgen05 kernel (needs k == 3, Ci % 32 == 0, Co in {32,64,128,256,512}). */
+size_t sx_conv2dmod_workspace_bytes(int B, int Ci, int Co, int H, int W, int k, int precision);
+int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, float* out,
+                     int B, int Ci, int Co, int H, int W, int k, int demod, float eps, int precision,
+                     void* workspace, size_t workspace_bytes, sx_stream_t stream);
+
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) -- ST:614,679.  [B,C,H,W] -> [B,C,2H,2W] */
+int sx_upsample2x_bilinear(const float* x, float* out, int B, int C, int H, int W, sx_stream_t stream);
+
+/* Blur.forward -- ST:144-153 (kornia filter2d, [1,2,1]x[1,2,1]/16, reflect border).  Same shape. */
+int sx_blur3x3_reflect(const float* x, float* out, int B, int C, int H, int W, sx_stream_t stream);
+
+/* GeneratorBlock noise + activation -- ST:696-698,705,714:
+ * out[b,c,y,x] = leaky_relu_0.2( x[b,c,y,x] + inoise[b|0, x, y] * noise_w[c] + noise_b[c] )
+ * inoise is the full-resolution map [noise_batch, noise_size, noise_size] (the trailing 1 of the
+ * reference's [B,S,S,1] dropped); note the TRANSPOSED spatial indexing of the reference (quirk Q1). */
+int sx_noise_lrelu(const float* x, const float* inoise, const float* noise_w, const float* noise_b, float* out,
+                   int B, int C, int H, int W, int noise_batch, int noise_size, sx_stream_t stream);
+
+/* RGBBlock tail -- ST:623-627: out = [blur(upsample2x(] rgb + prev [))].  prev may be NULL.
+ * rgb/prev [B,C,H,W]; out [B,C,2H,2W] when upsample != 0 else [B,C,H,W]. */
+int sx_rgb_add_upsample_blur(const float* rgb, const float* prev, float* out, int B, int C, int H, int W,
+                             int upsample, sx_stream_t stream);
+
+/* nn.Linear -- to_style1/2, RGBBlock.to_style (ST:608,681,685).  x[B,in], weight[out,in], bias[out] -> out[B,out] */
+int sx_linear_fwd(const float* x, const float* weight, const float* bias, float* out, int B, int in_features,
+                  int out_features, sx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generator plan -- sits under Generator.forward (ST:794-825) and the notebook's repeated
+ * stylex.G(w, noise) calls (NB:318,382).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* per-GeneratorBlock parameters, each a device pointer to an fp32 tensor laid out exactly as in the
+ * reference's state dict. */
+typedef struct sx_block_params {
+  const float* to_style1_w;  /* [Ci, latent]   blocks.i.to_style1.weight */
+  const float* to_style1_b;  /* [Ci]                                     */
+  const float* to_noise1_w;  /* [Co, 1]        blocks.i.to_noise1.weight */
+  const float* to_noise1_b;  /* [Co]                                     */
+  const float* conv1_w;      /* [Co, Ci, 3, 3] blocks.i.conv1.weight     */
+  const float* to_style2_w;  /* [Co, latent]                             */
+  const float* to_style2_b;  /* [Co]                                     */
+  const float* to_noise2_w;  /* [Co, 1]                                  */
+  const float* to_noise2_b;  /* [Co]                                     */
+  const float* conv2_w;      /* [Co, Co, 3, 3]                           */
+  const float* rgb_style_w;  /* [Co, latent]   blocks.i.to_rgb.to_style.weight */
+  const float* rgb_style_b;  /* [Co]                                     */
+  const float* rgb_conv_w;   /* [3, Co, 1, 1]  blocks.i.to_rgb.conv.weight */
+} sx_block_params;
+
+/* ci/co: host arrays of the (input_channels, filters) pair of each GeneratorBlock (ST:775-792);
+ * image_size = 4 << (num_blocks-1). */
+int sx_generator_create(const int* ci, const int* co, int num_blocks, int latent_dim, sx_generator_t** out);
+void sx_generator_destroy(sx_generator_t* g);
+
+/* Copy + pack the weights (fp32 [tap][Ci][Co] for the FFMA kernel, bf16 [Co][tap*Ci] K-major for the
+ * tcgen05 kernel, sum_k W^2 tables for demodulation), fold the batch-invariant
+ * initial_conv(initial_block) (ST:802,806, quirk Q13).  Synchronises `stream` before returning. */
+int sx_generator_load(sx_generator_t* g, const float* initial_block, const float* initial_conv_w,
+                      const float* initial_conv_b, const sx_block_params* blocks, sx_stream_t stream);
+
+/* StyleSpace width S = sum(Ci+Co) (the reference's num_style_coords, NB:471) and the width of the full
+ * per-sample style row  [ style coords (S) | ToRGB styles (sum Co) ]. */
+int sx_generator_num_style_coords(const sx_generator_t* g);
+int sx_generator_style_row(const sx_generator_t* g);
+
+/* K5: all W->S affine layers of all blocks at once.  w[B, num_blocks, latent] (the reference's `styles`
+ * argument) -> styles[B, style_row].  The first S columns are exactly Generator.forward's
+ * `style_coords` output (ST:709,821). */
+int sx_generator_styles(const sx_generator_t* g, const float* w, float* styles, int B, sx_stream_t stream);
+
+size_t sx_generator_workspace_bytes(const sx_generator_t* g, int max_batch, int precision);
+
+/* Generator.forward from StyleSpace.  styles[B, style_row]; inoise[noise_batch(1|B), S, S];
+ * rgb_out[B,3,S,S] fp32 NCHW, unclamped (ST:825).
+ *   start_conv == 0         : full forward.  If save_cache != 0 (requires B == 1) the raw input of every
+ *                             conv and every block's rgb are kept in the workspace (clean prefix).
+ *   start_conv == c (> 0)   : AttFind suffix: conv c = 2*block + {0: conv1, 1: conv2} is the first one
+ *                             whose style differs from the cached latent; everything before it is taken
+ *                             from the cache primed by the last save_cache call on this workspace. */
+int sx_generator_forward(sx_generator_t* g, const float* styles, const float* inoise, int noise_batch,
+                         float* rgb_out, int B, int start_conv, int save_cache, int precision,
+                         void* workspace, size_t workspace_bytes, sx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AttFind sweep + selection -- sits under attfind_extraction (NB:269-417) and
+ * find_significant_styles (NB:731-758).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* get_min_max_style_vectors -- NB:237-252.  style_coords[N, row_stride] (first S columns used). */
+int sx_attfind_minmax(const float* style_coords, int N, int S, int row_stride, float* minima, float* maxima,
+                      sx_stream_t stream);
+
+/* The shift injection of NB:358-381 for a whole batch of coord-evals of ONE latent:
+ * out[j, :] = base_row[:];  out[j, s_j] = base_row[s_j] + (m_dj[s_j] - base_row[s_j]) * shift_size
+ * with s_j = first_sindex + j / 2, d_j = j % 2 (0: towards minima, 1: towards maxima), j < 2*num_coords. */
+int sx_attfind_make_styles(const float* base_row, const float* minima, const float* maxima, float* out,
+                           int style_row, int first_sindex, int num_coords, float shift_size, sx_stream_t stream);
+
+/* NB:385: effects[n, d_j, s_j, :] = logits[j, :] - base_logits[n, :]  (effects [N,2,S,2], logits [2*num_coords, 2]) */
+int sx_attfind_scatter_effects(const float* logits, const float* base_logits, float* effects, int n, int S,
+                               int first_sindex, int num_coords, sx_stream_t stream);
+
+/* find_significant_styles -- NB:731-758 + the class split NB:695-714, on device.
+ * effects[N,2,S,2] (fp32, or fp64 when effects_f64 != 0 -- the notebook hands the function a float64 copy),
+ * base_logits[N,2] fp32 (label = argmax, first max wins) or NULL = every row belongs to `class_index` (the
+ * caller already split the classes, as the notebook does).  Greedy k rounds over the images of class
+ * `class_index`; column means accumulate in float64 in image order exactly like numpy.
+ * picks (device int32 [k*2]) receives (direction, sindex) pairs.  workspace: sx_attfind_select_workspace_bytes. */
+size_t sx_attfind_select_workspace_bytes(int N, int S);
+int sx_attfind_select(const void* effects, int effects_f64, const float* base_logits, int N, int S, int k,
+                      double max_image_effect, int class_index, int* picks, void* workspace, size_t workspace_bytes,
+                      sx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics
+ * ---------------------------------------------------------------------------------------------- */
+/* launches the tcgen05 kernel on a tiny problem and compares with the FFMA kernel; returns SX_OK when
+ * max-abs error <= tol.  Host-synchronous.  max_err_out (host pointer) may be NULL. */
+int sx_tc_selftest(float tol, float* max_err_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLEX_B200_H */

@@ -1,0 +1,356 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+
+Tolerances (BASELINE north_star): images max-abs <= 1e-4 in fp32, <= 2e-2 in bf16; selected top-k
+(direction, sindex) sets exact.  Nothing here reads /root/reference.
+"""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import stylex_b200 as sx
+from stylex_b200 import _native, synthetic
+from oracle import stylex_oracle as O
+from helpers import state_from_npz, tiny_cnn_from
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exact_torch():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    yield
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def tc_ok():
+    """Run the tcgen05 kernel once in a SUBPROCESS with a timeout: a trap or hang there must not take the
+    whole test process (or the box) with it."""
+    code = ("import sys; sys.path.insert(0, %r); import ctypes, stylex_b200; from stylex_b200 import _native as N; "
+            "e = ctypes.c_float(-1); rc = N.lib().sx_tc_selftest(5e-2, ctypes.byref(e)); "
+            "print('rc', rc, 'err', e.value, N.lib().sx_last_error().decode()); sys.exit(0 if rc == 0 else 3)" % ROOT)
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    except subprocess.TimeoutExpired:
+        return False, "tcgen05 selftest timed out"
+    return r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+
+
+def _need_tc(tc_ok):
+    ok, msg = tc_ok
+    if not ok:
+        pytest.fail("tcgen05 selftest failed, not launching bf16 kernels in-process: " + msg)
+
+
+def g_module(sd, size, cap, dev):
+    G = sx.Generator(size, 514, network_capacity=cap).to(dev)
+    missing, unexpected = G.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(".f") for k in missing)
+    return G
+
+
+# ------------------------------------------------------------------------------------------------
+# L1 ops (module level, NCHW fp32 boundary) vs the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Ci,Co,H,k,demod", [
+    (2, 16, 8, 8, 3, True), (3, 64, 64, 16, 3, True), (1, 32, 16, 32, 3, True), (2, 12, 20, 4, 3, True),
+    (2, 64, 3, 16, 1, False), (1, 8, 3, 64, 1, False), (5, 128, 64, 8, 3, False), (1, 512, 512, 4, 3, True)])
+def test_conv2dmod_fp32(dev, B, Ci, Co, H, k, demod):
+    g = torch.Generator().manual_seed(B * 1000 + Ci + Co + H)
+    x = torch.randn(B, Ci, H, H, generator=g)
+    y = torch.randn(B, Ci, generator=g)
+    m = sx.Conv2DMod(Ci, Co, k, demod=demod).to(dev)
+    ref = O.modconv(x, m.weight.detach().cpu(), y, demod=demod)
+    out = m(x.to(dev), y.to(dev)).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= FP32_TOL * max(1.0, ref.abs().max().item())
+
+
+def test_tcgen05_selftest(tc_ok):
+    ok, msg = tc_ok
+    assert ok, msg
+
+
+@pytest.mark.parametrize("B,Ci,Co,H", [(2, 64, 64, 16), (3, 32, 32, 8), (1, 64, 32, 64), (2, 512, 512, 4), (9, 256, 128, 4),
+                                        (1, 128, 64, 128), (2, 64, 32, 256)])
+def test_conv2dmod_bf16(dev, tc_ok, B, Ci, Co, H):
+    _need_tc(tc_ok)
+    g = torch.Generator().manual_seed(B * 1000 + Ci + Co + H)
+    x = torch.randn(B, Ci, H, H, generator=g)
+    y = torch.randn(B, Ci, generator=g) * 0.5
+    m = sx.Conv2DMod(Ci, Co, 3, precision="bf16").to(dev)
+    ref = O.modconv(x, m.weight.detach().cpu(), y, demod=True)
+    out = m(x.to(dev), y.to(dev)).cpu()
+    # demodulated outputs are O(1); bf16 inputs with fp32 accumulation
+    assert (out - ref).abs().max().item() <= BF16_TOL * max(1.0, ref.abs().max().item())
+
+
+def test_conv2dmod_bf16_unsupported_shape_is_an_error(dev):
+    m = sx.Conv2DMod(12, 20, 3, precision="bf16").to(dev)
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        m(torch.randn(1, 12, 8, 8, device=dev), torch.randn(1, 12, device=dev))
+
+
+def test_cpu_tensor_is_an_error():
+    m = sx.Conv2DMod(8, 8, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 8, 4, 4), torch.randn(1, 8))
+
+
+def test_upsample_blur_noise_linear(dev):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 5, 8, 8, generator=g)
+    up = sx.modules.upsample2x(x.to(dev)).cpu()
+    assert (up - O.upsample2x(x)).abs().max().item() <= 1e-6
+    bl = sx.Blur().to(dev)(x.to(dev)).cpu()
+    assert (bl - O.blur3x3_reflect(x)).abs().max().item() <= 1e-6
+    lin = torch.nn.Linear(1, 5)
+    inoise = torch.rand(3, 16, 16, 1, generator=g)
+    for nz in (inoise, inoise[:1]):
+        ref = O.leaky_relu(x + lin(nz[:, :8, :8, :]).permute((0, 3, 2, 1)))
+        out = sx.modules.noise_lrelu(x.to(dev), nz.to(dev), lin.to(dev)).cpu()
+        lin = lin.cpu()
+        assert (out - ref).abs().max().item() <= 1e-6
+    w, b = torch.randn(7, 514, generator=g), torch.randn(7, generator=g)
+    xi = torch.randn(4, 514, generator=g)
+    out = sx.modules.linear(xi.to(dev), w.to(dev), b.to(dev)).cpu()
+    assert (out - torch.nn.functional.linear(xi, w, b)).abs().max().item() <= 2e-5
+
+
+def test_rgb_block_and_generator_block(dev):
+    sd = synthetic.make_generator_state(16, seed=9, network_capacity=4)   # blocks (32,32) (32,16) (16,8)
+    G = g_module(sd, 16, 4, dev)
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(2, 514, generator=g)
+    noise = torch.rand(1, 16, 16, 1, generator=g)
+    x = torch.randn(2, 32, 4, 4, generator=g)
+    prev = torch.randn(2, 3, 8, 8, generator=g)
+    xr, rgbr, scr = O.generator_block(sd, 1, x, prev, w, noise, upsample=True, upsample_rgb=True)
+    xo, rgbo, sco = G.blocks[1](x.to(dev), prev.to(dev), w.to(dev), noise.to(dev))
+    assert (xo.cpu() - xr).abs().max().item() <= FP32_TOL
+    assert (rgbo.cpu() - rgbr).abs().max().item() <= FP32_TOL
+    assert (sco.cpu() - scr).abs().max().item() <= 2e-5
+    # last block: no rgb upsample, first block: no feature upsample / no prev
+    x0 = torch.randn(2, 32, 4, 4, generator=g)
+    xr, rgbr, _ = O.generator_block(sd, 0, x0, None, w, noise, upsample=False, upsample_rgb=True)
+    xo, rgbo, _ = G.blocks[0](x0.to(dev), None, w.to(dev), noise.to(dev))
+    assert (xo.cpu() - xr).abs().max().item() <= FP32_TOL and (rgbo.cpu() - rgbr).abs().max().item() <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# Generator.forward vs the golden images produced by the reference itself
+# ------------------------------------------------------------------------------------------------
+def test_generator_small_fp32_vs_reference_golden(dev, golden):
+    z = golden("gen_small.npz")
+    sd = state_from_npz(z, "G.")
+    G = g_module(sd, 32, 4, dev)
+    w = torch.from_numpy(z["latents"]).to(dev)
+    noise = torch.from_numpy(z["noise"]).to(dev)
+    img, sc = G(sx.styles_def_to_tensor([(w, G.num_layers)]), noise, get_style_coords=True)
+    assert np.abs(img.cpu().numpy() - z["image"]).max() <= FP32_TOL
+    assert np.abs(sc.cpu().numpy() - z["style_coords"]).max() <= 2e-5
+    img2, sc2 = G(torch.from_numpy(z["styles_per_layer"]).to(dev), noise, get_style_coords=True)
+    assert np.abs(img2.cpu().numpy() - z["image_per_layer"]).max() <= FP32_TOL
+    assert np.abs(sc2.cpu().numpy() - z["style_coords_per_layer"]).max() <= 2e-5
+    # per-sample noise maps (input_noise batch == B) behave like the broadcast one when they are equal
+    img3 = G(sx.styles_def_to_tensor([(w, G.num_layers)]), noise.expand(w.shape[0], -1, -1, -1).contiguous())
+    assert torch.equal(img3, img)
+
+
+@pytest.mark.parametrize("size", [64, 256])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_generator_full_vs_reference_golden(dev, golden, tc_ok, size, precision):
+    if precision == "bf16":
+        _need_tc(tc_ok)
+    z = golden("gen_full.npz")
+    sd = synthetic.make_generator_state(size, seed=42)
+    n = z[f"image_{size}"].shape[0]
+    G = g_module(sd, size, 16, dev)
+    G.precision = precision
+    w = synthetic.make_latents(n, 42).to(dev)
+    noise = synthetic.make_noise(size, 42).to(dev)
+    img, sc = G(sx.styles_def_to_tensor([(w, G.num_layers)]), noise, get_style_coords=True)
+    err = np.abs(img.cpu().numpy() - z[f"image_{size}"]).max()
+    print(f"generator {size}px {precision}: max-abs image error {err:.3e} (max|img| {np.abs(z[f'image_{size}']).max():.2f})")
+    assert err <= (FP32_TOL if precision == "fp32" else BF16_TOL)
+    assert np.abs(sc.cpu().numpy() - z[f"style_coords_{size}"]).max() <= 5e-5
+    assert sc.shape[1] == {64: 2464, 256: 4512}[size]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_suffix_forward_equals_full_forward(dev, tc_ok, precision):
+    """clean-prefix reuse must not change the result: for every conv c, re-running only the suffix from c with a
+    perturbed style row equals the full forward with that row (same kernels downstream => tight tolerance)."""
+    if precision == "bf16":
+        _need_tc(tc_ok)
+    size, cap = 32, 16   # channels 128/64/32: eligible for the tensor-core kernel
+    sd = synthetic.make_generator_state(size, seed=21, network_capacity=cap)
+    G = g_module(sd, size, cap, dev)
+    plan = G.plan()
+    w = synthetic.make_latents(1, 21).to(dev)
+    noise = synthetic.make_noise(size, 21).to(dev)
+    base = plan.styles(sx.styles_def_to_tensor([(w, G.num_layers)]).contiguous())
+    plan.reserve(8, precision)
+    plan.forward(base, noise, save_cache=True, precision=precision)
+    for conv, (off, width) in enumerate(plan.conv_coords):
+        rows = base.repeat(4, 1)
+        for j in range(4):
+            rows[j, off + (j * 7) % width] += 0.5 * (j + 1)
+        full = plan.forward(rows, noise, precision=precision)
+        # the full forward did not touch the cache (save_cache=False)
+        suffix = plan.forward(rows, noise, start_conv=conv, precision=precision)
+        tol = 1e-5 if precision == "fp32" else 2e-2
+        assert (full - suffix).abs().max().item() <= tol, conv
+
+
+# ------------------------------------------------------------------------------------------------
+# the sweep and the selection
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["mobilenet", "resnet"])
+def test_attfind_sweep_small_vs_verbatim_notebook_golden(dev, golden, kind):
+    z = golden("attfind_small.npz")
+    sd = state_from_npz(z, "G.")
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    G = g_module(sd, size, cap, dev)
+    clf = sx.make_classifier(kind, tiny_cnn_from(z, f"{kind}.clf.").to(dev), size)
+    latents = torch.from_numpy(z[f"{kind}.latents"]).to(dev)
+    noise = torch.from_numpy(z["noise"]).to(dev)
+    res = sx.attfind_sweep(G, clf, latents, noise, shift_size=1.0, precision="fp32", max_batch=64)
+    assert np.abs(res["style_coordinates"].cpu().numpy() - z[f"{kind}.style_coordinates"]).max() <= 2e-5
+    assert np.abs(res["base_prob"].cpu().numpy() - z[f"{kind}.base_prob"]).max() <= 2e-4
+    assert np.abs(res["minima"].cpu().numpy() - z[f"{kind}.minima"][0]).max() <= 2e-5
+    assert np.abs(res["maxima"].cpu().numpy() - z[f"{kind}.maxima"][0]).max() <= 2e-5
+    err = np.abs(res["style_change"].cpu().numpy() - z[f"{kind}.style_change"]).max()
+    print(f"sweep {kind}: max|effect error| {err:.3e} vs max|effect| {np.abs(z[f'{kind}.style_change']).max():.3f}")
+    assert err <= 3e-4
+    picks, merged, _ = sx.attfind_select(res["style_change"], res["base_prob"], 5, 0.5)
+    assert picks[0] == [tuple(p) for p in z[f"{kind}.picks0"]]
+    assert picks[1] == [tuple(p) for p in z[f"{kind}.picks1"]]
+    assert merged == [tuple(p) for p in z[f"{kind}.merged"]]
+
+
+def test_select_kernel_cases_exact(dev, golden):
+    z = golden("select_cases.npz")
+    for name in z["cases"]:
+        eff = z[f"{name}.effects"]
+        mie, k = z[f"{name}.params"]
+        for c in (0, 1):
+            got = sx.find_significant_styles(eff, int(k), c, None, None, None, None, None, max_image_effect=float(mie))
+            assert got == [tuple(p) for p in z[f"{name}.picks{c}"]], (name, c)
+    # sindex_offset and tensor input
+    eff = torch.from_numpy(z["plain.effects"]).to(dev)
+    got = sx.find_significant_styles(eff, 3, 0, max_image_effect=2.5, sindex_offset=10)
+    assert got == [(d, s + 10) for d, s in [tuple(p) for p in z["plain.picks0"]][:3]]
+
+
+def test_select_with_class_split_matches_oracle(dev):
+    rng = np.random.RandomState(5)
+    for N, S in ((64, 300), (7, 33), (200, 1000)):
+        eff = (rng.randn(N, 2, S, 2) * 0.6).astype(np.float32)
+        base = rng.randn(N, 2).astype(np.float32)
+        base[3] = base[3, 0]  # a tie in the logits: np.argmax picks class 0
+        picks_ref, merged_ref, _ = O.attfind_select(eff, base, 5, 0.5)
+        picks, merged, _ = sx.attfind_select(torch.from_numpy(eff).to(dev), torch.from_numpy(base).to(dev), 5, 0.5)
+        assert picks == picks_ref and merged == merged_ref
+
+
+def test_select_empty_class_raises(dev):
+    eff = torch.zeros(4, 2, 6, 2, device=dev)
+    base = torch.tensor([[1.0, 0.0]] * 4, device=dev)
+    with pytest.raises(IndexError):
+        sx.attfind_select(eff, base, 2, 0.5)
+
+
+def _config64(dev, kind, n_lat):
+    sd = synthetic.make_generator_state(64, seed=42)
+    G = g_module(sd, 64, 16, dev)
+    lat = synthetic.make_latents(n_lat, 42)
+    noise = synthetic.make_noise(64, 42)
+    model = synthetic.make_classifier_model(kind, 42)
+    clf_cpu = sx.make_classifier(kind, model, 64)
+    L = len(O.generator_layout(sd))
+    calib = O.generator_forward(sd, O.styles_def_to_tensor([(synthetic.make_latents(16, 7), L)]), noise)
+    synthetic.calibrate_classifier(model, clf_cpu.preprocess, calib, target_std=1.0, chunk=8)
+    clf_gpu = sx.make_classifier(kind, copy.deepcopy(model).to(dev), 64)
+    return sd, G, lat, noise, clf_cpu, clf_gpu
+
+
+@pytest.mark.parametrize("kind", ["mobilenet", "resnet"])
+def test_attfind_sweep_64px_subset_vs_oracle(dev, kind):
+    """BASELINE config shapes (64px generator, real torchvision classifier), bounded: 2 latents x 24 coordinates spread
+    over every conv x 2 directions, oracle = batch-1 full forwards on the CPU."""
+    sd, G, lat, noise, clf_cpu, clf_gpu = _config64(dev, kind, 2)
+    S = G.num_style_coords
+    sind = sorted(set(list(range(0, S, 107)) + [S - 1, 1023, 1024, 2367, 2368]))
+    ref = O.attfind_sweep(sd, clf_cpu.classify_images, lat, noise, sindices=sind)
+    res = sx.attfind_sweep(G, clf_gpu, lat.to(dev), noise.to(dev), precision="fp32", sindices=sind, max_batch=32)
+    err = (res["style_change"].cpu() - ref["style_change"]).abs().max().item()
+    mag = ref["style_change"].abs().max().item()
+    print(f"64px {kind}: max|effect err| {err:.3e}, max|effect| {mag:.3e}")
+    assert mag > 1e-3, "degenerate classifier: effects are ~0"
+    assert err <= 1e-3 * max(1.0, mag)
+    assert (res["base_prob"].cpu() - ref["base_prob"]).abs().max().item() <= 1e-3
+
+
+def test_attfind_bf16_sweep_close_to_fp32(dev, tc_ok):
+    _need_tc(tc_ok)
+    sd, G, lat, noise, clf_cpu, clf_gpu = _config64(dev, "resnet", 1)
+    S = G.num_style_coords
+    sind = list(range(0, S, 61))
+    r32 = sx.attfind_sweep(G, clf_gpu, lat.to(dev), noise.to(dev), precision="fp32", sindices=sind, max_batch=32)
+    r16 = sx.attfind_sweep(G, clf_gpu, lat.to(dev), noise.to(dev), precision="bf16", sindices=sind, max_batch=32)
+    err = (r32["style_change"] - r16["style_change"]).abs().max().item()
+    mag = r32["style_change"].abs().max().item()
+    print(f"bf16 vs fp32 effects: max err {err:.3e}, max|effect| {mag:.3e}")
+    assert err <= 0.1 * max(mag, 1e-2)
+
+
+def test_attfind_extraction_entry_point(dev, tmp_path):
+    """the notebook-signature entry point end to end on a tiny model, writing the 9 datasets."""
+    size, cap = 16, 4
+    sd = synthetic.make_generator_state(size, seed=11, network_capacity=cap)
+    G = g_module(sd, size, cap, dev)
+
+    class Enc(torch.nn.Module):
+        def forward(self, img):
+            return torch.nn.functional.adaptive_avg_pool2d(img, 16).reshape(-1)[:512] * 0.5
+
+    class Stylex:
+        pass
+
+    st = Stylex()
+    st.G, st.encoder, st.D = G, Enc(), None
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                                torch.nn.Linear(4, 2)).to(dev).eval()
+    clf = sx.make_classifier("mobilenet", model, size)
+    images = [torch.rand(1, 3, size, size) for _ in range(3)]
+    noise = synthetic.make_noise(size, 1).to(dev)
+    out = sx.attfind_extraction(images, 3, str(tmp_path), st, clf, None, noise, G.num_style_coords, 1, -0.5,
+                                image_size=size, batch_size=1, cuda_rank=0)
+    assert set(out) == set(sx.attfind.DATASET_NAMES)
+    assert out["style_change"].shape == (3, 2, G.num_style_coords, 2)
+    f = [p for p in os.listdir(tmp_path) if p.startswith("style_change_records")]
+    assert len(f) == 1
+    with pytest.raises(ValueError):
+        sx.attfind_extraction(images, 3, None, st, clf, None, noise, 2464, 1, -0.5, image_size=size)
+
+
+def test_native_launches_counted(dev):
+    before = _native.launch_count()
+    sx.modules.upsample2x(torch.zeros(1, 1, 4, 4, device=dev))
+    assert _native.launch_count() == before + 1

@@ -1,0 +1,167 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol (no compute without a GPU), the host
+logic (coordinate runs, sharding, gloo gather), synthetic inputs, state-dict compatibility."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import stylex_b200 as sx
+from stylex_b200 import _native, attfind, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "stylex_b200.h")).read()
+    declared = set(re.findall(r"\b(sx_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _native.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/stylex_b200.h but not exported"
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert lib.sx_version() == 100
+    assert lib.sx_generator_workspace_bytes(None, 1, 0) == 0
+
+
+def test_no_silent_cpu_path():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sx.modules.upsample2x(torch.zeros(1, 1, 2, 2))
+    G = sx.Generator(16, 514, network_capacity=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G(torch.zeros(1, 3, 514), torch.zeros(1, 16, 16, 1))
+    with pytest.raises(NotImplementedError):
+        sx.Generator(16, 514, transparent=True)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "explaining-in-style-reproducibility-study_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_state_dict_keys_match_reference_layout():
+    G = sx.Generator(64, 514)
+    keys = list(G.state_dict().keys())
+    assert len(keys) == 72
+    for k in ("initial_block", "initial_conv.weight", "initial_conv.bias", "blocks.0.to_style1.weight",
+              "blocks.0.to_noise1.weight", "blocks.0.conv1.weight", "blocks.4.to_rgb.conv.weight",
+              "blocks.4.to_rgb.to_style.bias", "blocks.0.to_rgb.upsample.1.f"):
+        assert k in keys, k
+    assert "blocks.4.to_rgb.upsample.1.f" not in keys         # last block has no rgb upsample
+    assert G.num_style_coords == 2464 and sx.Generator(256, 514).num_style_coords == 4512
+    sd = synthetic.make_generator_state(64)
+    missing, unexpected = G.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(".f") for k in missing)
+    b = G.blocks[1]
+    assert (b.input_channels, b.filters, b.num_style_coords) == (512, 256, 768)
+    assert attfind.sindex_to_block_idx_and_index(G, 1024) == (1, 0)
+    assert attfind.sindex_to_block_idx_and_index(G, 2463) == (4, 95)
+
+
+def test_coord_runs_cover_every_coordinate_once():
+    pairs = synthetic.generator_pairs(64)
+    conv_coords, off = [], 0
+    for ci, co in pairs:
+        conv_coords += [(off, ci), (off + ci, co)]
+        off += ci + co
+    runs = attfind._coord_runs(conv_coords, None, 64)
+    seen = []
+    for conv, first, cnt in runs:
+        o, w = conv_coords[conv]
+        assert o <= first and first + cnt <= o + w and 1 <= cnt <= 64
+        seen += list(range(first, first + cnt))
+    assert seen == list(range(2464))
+    sub = [0, 1, 2, 5, 511, 512, 513, 2463]
+    runs = attfind._coord_runs(conv_coords, sub, 2)
+    got = sorted(s for _, f, c in runs for s in range(f, f + c))
+    assert got == sorted(sub)
+    assert all(c <= 2 for _, _, c in runs)
+    for conv, first, cnt in runs:
+        o, w = conv_coords[conv]
+        assert o <= first and first + cnt <= o + w
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 8, 1024, 1030):
+        for world in (1, 2, 3, 8):
+            r = [attfind.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_inputs_are_deterministic():
+    a = synthetic.make_generator_state(16, seed=3, network_capacity=4)
+    b = synthetic.make_generator_state(16, seed=3, network_capacity=4)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(synthetic.make_latents(4, 1), synthetic.make_latents(4, 1))
+    assert synthetic.make_noise(16).shape == (1, 16, 16, 1)
+    m1, m2 = synthetic.make_classifier_model("resnet", 1), synthetic.make_classifier_model("resnet", 1)
+    assert all(torch.equal(p, q) for p, q in zip(m1.state_dict().values(), m2.state_dict().values()))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+import stylex_b200 as sx
+from stylex_b200 import dist as sxd, attfind
+rank, world, _ = sxd.init_from_env("gloo")
+N, S = {n}, 5
+lo, hi = attfind.shard_range(N, rank, world)
+full = torch.arange(N * 2 * S * 2, dtype=torch.float32).reshape(N, 2, S, 2)
+out = sxd.gather_effects(full[lo:hi].clone(), N, world)
+assert out.shape == full.shape, out.shape
+assert torch.equal(out, full), rank
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+@pytest.mark.parametrize("n", [8, 7])
+def test_gather_effects_world_size_2_gloo(tmp_path, n):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT, n=n))
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs), outs
+
+
+def test_classifier_wrappers_match_reference_semantics():
+    """resize-to-224 + normalise (ResNet) / interpolate-to-image_size + normalise (MobileNet), raw logits out."""
+    import torchvision
+    from torchvision.transforms.functional import resize
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(3, 2)).eval()
+    x = torch.rand(2, 3, 64, 64) * 3 - 1
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    r = sx.ResNet(model=net, image_size=64)
+    assert torch.allclose(r.classify_images(x), net((resize(x, [224, 224]) - mean) / std), atol=1e-6)
+    m = sx.MobileNet(model=net, image_size=64)
+    assert torch.allclose(m.classify_images(x), net((x - mean) / std), atol=1e-6)
+    assert r.resnet_dim == 224 and m.image_size == 64 and r.normalize

@@ -1,0 +1,54 @@
+"""Runs only where the reference checkout exists (the build container): the oracle and the product's classifier
+wrappers against the UNMODIFIED reference code, beyond what the committed fixtures cover."""
+import numpy as np
+import pytest
+import torch
+
+import stylex_b200 as sx
+from stylex_b200 import synthetic
+from oracle import ref_loader as RL, stylex_oracle as O
+
+pytestmark = pytest.mark.skipif(not RL.available(), reason="reference checkout not present (GPU box)")
+torch.set_grad_enabled(False)
+
+
+def test_oracle_ops_bit_match_reference_modules():
+    R = RL.load_reference()
+    g = torch.Generator().manual_seed(0)
+    for ci, co, k, demod in ((8, 12, 3, True), (16, 3, 1, False)):
+        m = R.Conv2DMod(ci, co, k, demod=demod)
+        x, y = torch.randn(2, ci, 8, 8, generator=g), torch.randn(2, ci, generator=g)
+        assert torch.equal(m(x, y), O.modconv(x, m.weight.detach(), y, demod=demod))
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    assert torch.equal(R.Blur()(x), O.blur3x3_reflect(x))
+
+
+def test_oracle_generator_matches_reference_with_shift():
+    """the oracle's functional coord_shift == the notebook's `bias += shift` patch (NB:381) up to fp32 rounding."""
+    sd = synthetic.make_generator_state(16, seed=2, network_capacity=4)
+    G = RL.reference_generator(sd, 16, network_capacity=4)
+    w = synthetic.make_latents(1, 2)
+    noise = synthetic.make_noise(16, 2)
+    styles = O.styles_def_to_tensor([(w, G.num_layers)])
+    S = O.num_style_coords(sd)
+    for sindex in (0, 31, 32, 70, S - 1):
+        shift = torch.zeros(1, S)
+        shift[0, sindex] = 0.7
+        mine = O.generator_forward(sd, styles, noise, coord_shift=shift)
+        blk, idx = O.sindex_to_block_idx_and_index(O.generator_layout(sd), sindex)
+        b = G.blocks[blk]
+        layer, j = (b.to_style1, idx) if idx < b.input_channels else (b.to_style2, idx - b.input_channels)
+        layer.bias[j] += 0.7
+        ref = G(styles, noise)
+        layer.bias[j] -= 0.7
+        assert (ref - mine).abs().max().item() <= 2e-6
+
+
+def test_product_classifier_wrappers_match_reference_wrappers():
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(4, 2)).eval()
+    x = torch.rand(2, 3, 64, 64) * 2 - 0.5
+    for kind in ("resnet", "mobilenet"):
+        ref = RL.reference_classifier(kind, net, 64).classify_images(x)
+        mine = sx.make_classifier(kind, net, 64).classify_images(x)
+        assert torch.equal(ref, mine), kind
