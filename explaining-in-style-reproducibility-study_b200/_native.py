@@ -63,6 +63,8 @@ SIGNATURES = {
     "sx_attfind_select": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
     "sx_tc_selftest": (c_int, [c_float, POINTER(c_float)]),
+    "sx_profile_enable": (c_int, [c_int]),
+    "sx_profile_collect": (c_int, [POINTER(c_double), c_int, POINTER(c_int)]),
 }
 
 _lib = None
@@ -128,6 +130,19 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().sx_profile_enable(1 if on else 0), "sx_profile_enable")
+
+
+def profile_collect() -> dict:
+    """{kind: {"launches", "ms", "flops", "bytes"}} since profile_enable(True); synchronises the recorded events."""
+    rows = (c_double * (5 * 64))()
+    n = c_int(0)
+    check(lib().sx_profile_collect(rows, 64, byref(n)), "sx_profile_collect")
+    return {int(rows[5 * i]): {"launches": int(rows[5 * i + 1]), "ms": rows[5 * i + 2], "flops": rows[5 * i + 3],
+                               "bytes": rows[5 * i + 4]} for i in range(n.value)}
 
 
 def launch_count() -> int:

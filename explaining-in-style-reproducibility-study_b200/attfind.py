@@ -84,7 +84,8 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.Tensor, shift_size: float = 1.0,
                   precision: Optional[str] = None, max_batch: int = 128, rank: int = 0, world_size: int = 1,
                   sindices: Optional[Sequence[int]] = None, image_indices: Optional[Sequence[int]] = None,
-                  gather: bool = True, stats: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                  gather: bool = True, stats: Optional[dict] = None,
+                  minmax: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """Phases A(second half)-C of ``attfind_extraction`` (NB:316-389) for latents ``[N, latent]``.
 
     Every rank computes the style coordinates, base images and base logits of ALL N latents (cheap, and it
@@ -94,7 +95,9 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     [N,2] (raw logits, quirk Q3), 'style_coordinates' [N,S], 'minima' / 'maxima' [S], 'latents'.
 
     ``sindices`` / ``image_indices`` restrict the sweep to a subset (bounded benchmark / test samples);
-    untouched entries of 'style_change' stay 0.
+    untouched entries of 'style_change' stay 0.  ``minmax`` = (minima, maxima) [S] supplies the global
+    per-coordinate extrema when ``latents`` is only a slice of the job (they must come from ALL latents,
+    NB:340); by default they are computed from ``latents``.
     """
     precision = precision or G.precision
     N.require_cuda(latents, noise)
@@ -116,10 +119,16 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     for i in range(0, n_all, max_batch):                                                # NB:316-334, batched
         rgb = plan.forward(styles_all[i: i + max_batch].contiguous(), noise, precision=precision)
         base_logits[i: i + max_batch] = classifier.classify_images(rgb).float()
-    minima = torch.empty(S, device=dev, dtype=torch.float32)
-    maxima = torch.empty_like(minima)
-    N.check(lib.sx_attfind_minmax(styles_all.data_ptr(), n_all, S, row, minima.data_ptr(), maxima.data_ptr(), stream),
-            "sx_attfind_minmax")                                                        # NB:340
+    if minmax is None:
+        minima = torch.empty(S, device=dev, dtype=torch.float32)
+        maxima = torch.empty_like(minima)
+        N.check(lib.sx_attfind_minmax(styles_all.data_ptr(), n_all, S, row, minima.data_ptr(), maxima.data_ptr(), stream),
+                "sx_attfind_minmax")                                                    # NB:340
+    else:
+        minima, maxima = (N.f32c(t) for t in minmax)
+        N.require_cuda(minima, maxima)
+        if minima.shape != (S,) or maxima.shape != (S,):
+            raise ValueError(f"minmax must be two [{S}] tensors")
 
     lo, hi = shard_range(n_all, rank, world_size)
     mine = list(range(lo, hi))

@@ -48,11 +48,28 @@ class _Wrapper:
         self.model.to(device)
         return self
 
+    def set_compute(self, dtype: torch.dtype = torch.float32, channels_last: bool = False):
+        """Throughput knobs of the PyTorch classifier: parameter/activation dtype and memory format.  The resize and
+        normalisation stay fp32 exactly as in the reference wrapper; logits are returned as fp32."""
+        self.compute_dtype = dtype
+        self.channels_last = channels_last
+        self.model.to(dtype)
+        if channels_last:
+            self.model.to(memory_format=torch.channels_last)
+        return self
+
     def preprocess(self, images: torch.Tensor) -> torch.Tensor:
         raise NotImplementedError
 
+    compute_dtype = torch.float32
+    channels_last = False
+
     def classify_images(self, images) -> torch.Tensor:
-        return self.model(self.preprocess(images))
+        x = self.preprocess(images)
+        if self.compute_dtype != torch.float32 or self.channels_last:
+            x = x.to(dtype=self.compute_dtype, memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+            return self.model(x).float()
+        return self.model(x)
 
     __call__ = classify_images
 

@@ -299,6 +299,44 @@ int sx_attfind_select(const void* effects, int effects_f64, const float* base_lo
 }
 
 // -------------------------------------------------------------------------------------------------
+// per-kernel timing for bench.py
+// -------------------------------------------------------------------------------------------------
+int sx_profile_enable(int on) {
+  Profiler& p = profiler();
+  std::lock_guard<std::mutex> g(p.m);
+  for (auto& r : p.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  p.recs.clear();
+  p.on = on != 0;
+  return SX_OK;
+}
+
+int sx_profile_collect(double* rows, int max_rows, int* n_rows) {
+  SX_REQUIRE(rows && n_rows && max_rows >= 1, "bad argument");
+  Profiler& p = profiler();
+  std::lock_guard<std::mutex> g(p.m);
+  std::map<int, std::vector<double>> agg;  // kind -> launches, ms, flops, bytes
+  for (auto& r : p.recs) {
+    SX_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    SX_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    auto& a = agg[r.kind];
+    if (a.empty()) a.assign(4, 0.0);
+    a[0] += 1; a[1] += ms; a[2] += r.flops; a[3] += r.bytes;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  p.recs.clear();
+  int n = 0;
+  for (auto& kv : agg) {
+    if (n >= max_rows) break;
+    rows[5 * n] = kv.first;
+    for (int j = 0; j < 4; ++j) rows[5 * n + 1 + j] = kv.second[j];
+    ++n;
+  }
+  *n_rows = n;
+  return SX_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // diagnostics: tcgen05 kernel vs FFMA kernel on small problems (host synchronous)
 // -------------------------------------------------------------------------------------------------
 static int selftest_case(int B, int Ci, int Co, int H, float* max_err) {

@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(256) upsample2x_modulate_kernel(const T* __res
 #pragma unroll
     for (int j = 0; j < V; ++j) o[j] = ly0 * (lx0 * f00[j] + lx1 * f01[j]) + ly1 * (lx0 * f10[j] + lx1 * f11[j]);
     if (style) {
+      // round to the storage type first: identical to upsample -> cache -> modulate of the AttFind suffix path
       const float* s = style + (long long)b * style_stride + c;
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] *= __ldg(s + j) + 1.f;
+      for (int j = 0; j < V; ++j) o[j] = to_f(from_f<T>(o[j])) * (__ldg(s + j) + 1.f);
     }
     vec_t v;
     pack(o, v);

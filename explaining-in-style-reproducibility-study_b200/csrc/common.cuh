@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <vector>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -82,6 +85,41 @@ inline int ew_grid(long long work_items, int threads, int ctas_per_sm = 8) {
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream -------------
+// kinds: 0..19 conv index of the generator plan, 32 modulate, 33 upsample, 34 torgb, 35 demod, 36 styles,
+//        40 make_styles, 41 scatter, 42 select, 43 minmax, 50 op-level conv, 51 other op-level
+struct ProfRec {
+  int kind;
+  double flops, bytes;
+  cudaEvent_t a, b;
+};
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::mutex m;
+};
+inline Profiler& profiler() {
+  static Profiler p;
+  return p;
+}
+struct ProfScope {
+  bool active;
+  ProfRec r;
+  cudaStream_t st;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t s) : active(profiler().on), st(s) {
+    if (!active) return;
+    r.kind = kind; r.flops = flops; r.bytes = bytes;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { active = false; return; }
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> g(profiler().m);
+    profiler().recs.push_back(r);
+  }
+};
 
 // ---- element types -----------------------------------------------------------------------------
 template <typename T>

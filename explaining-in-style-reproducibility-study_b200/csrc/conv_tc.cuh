@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         float t = __uint_as_float(v[j]) * dd[c0 + j];
         t += nz * s_nw[c0 + j] + s_nb[c0 + j];
         if (ep.act) t = lrelu02(t);
+        // round the raw activation to the storage type BEFORE the next layer's modulation: the AttFind suffix path
+        // re-modulates the cached (bf16) raw tensor, and both paths must produce bit-identical conv inputs
+        if (!ep.out_nchw_f32) t = __bfloat162float(__float2bfloat16_rn(t));
         fr[j] = t;
         f[j] = t * mm[c0 + j];
       }

@@ -195,11 +195,13 @@ inline int run_conv<float>(const sx_generator* g, int conv_idx, const float* x, 
   ConvSimtParams p;
   p.x = x; p.x_bstride = (long long)H * H * Ci; p.wpk = g->conv[conv_idx].wpk;
   p.B = B; p.Ci = Ci; p.Co = Co; p.H = H; p.W = H; p.KS = 3; p.ep = ep;
+  ProfScope ps(conv_idx, 2.0 * 9 * Ci * Co * (double)H * H * B, 4.0 * B * H * H * (Ci + Co), st);
   return launch_conv_simt(p, st);
 }
 template <>
 inline int run_conv<__nv_bfloat16>(const sx_generator* g, int conv_idx, const __nv_bfloat16* x, int B, int Ci, int Co, int H,
                                    const ConvEpilogue& ep, cudaStream_t st) {
+  ProfScope ps(conv_idx, 2.0 * 9 * Ci * Co * (double)H * H * B, 2.0 * B * H * H * (Ci + Co), st);
   return tc::launch_conv_tc(x, g->conv[conv_idx].wbf, B, Ci, Co, H, H, 3, ep, st);
 }
 
@@ -235,6 +237,7 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
     dp.dcoef = dcoef;
     dp.dcoef_stride = g->demod_row;
     dp.eps = 1e-8f;
+    ProfScope ps(35, 0, 0, st);
     dim3 grid((max_co + 127) / 128, B, dp.num_convs);
     demod_kernel<<<grid, 128, max_ci * sizeof(float), st>>>(dp);
     SX_CHECK_LAUNCH();
@@ -263,12 +266,14 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
         if (l == 0 && save_cache) {
           SX_CUDA(cudaMemcpyAsync(cache_in(0), x0, (size_t)HW * ci * sizeof(T), cudaMemcpyDeviceToDevice, st));
         }
+        ProfScope ps(32, 0, (double)sizeof(T) * B * HW * ci, st);
         SX_TRY(launch_modulate<T>(src, 0, styles + g->soff1[l], row, xin, B, HW, ci, st));
       } else if (save_cache) {
         // keep the raw upsampled tensor for the sweep, then modulate it
         SX_TRY(launch_upsample2x_modulate<T>(y2, HW / 4 * ci, nullptr, 0, cache_in(2 * l), B, H / 2, H / 2, ci, st));
         SX_TRY(launch_modulate<T>(cache_in(2 * l), HW * ci, styles + g->soff1[l], row, xin, B, HW, ci, st));
       } else {
+        ProfScope ps(33, 0, (double)sizeof(T) * B * HW * ci * 1.25, st);
         SX_TRY(launch_upsample2x_modulate<T>(y2, HW / 4 * ci, styles + g->soff1[l], row, xin, B, H / 2, H / 2, ci, st));
       }
       // ---- conv1: y1m = lrelu(d1 * conv + noise1) * (style2 + 1)
@@ -280,6 +285,7 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
       SX_TRY(run_conv<T>(g, 2 * l, xin, B, ci, co, H, ep, st));
     } else {
       // sweep starts at conv2 of this block: its raw input comes from the cache
+      ProfScope ps(32, 0, (double)sizeof(T) * B * HW * co, st);
       SX_TRY(launch_modulate<T>(cache_in(2 * l + 1), 0, styles + g->soff2[l], row, y1m, B, HW, co, st));
     }
     // ---- conv2: y2 = lrelu(d2 * conv + noise2)
@@ -292,7 +298,10 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
     float* rgb_dst = (l == nb - 1) ? rgb_out : ((l & 1) ? rgb_pong : rgb_ping);
     if (l != nb - 1 && (size_t)B * 3 * HW * 4 > ((l & 1) ? (L.total - L.rgb_b) : (L.rgb_b - L.rgb_a)))
       return fail(SX_ENOMEM, "internal: rgb scratch too small");
-    SX_TRY(launch_torgb<T>(y2, styles + g->soffr[l], row, g->wrgb[l], prev_rgb, prev_bstride, rgb_dst, B, H, H, co, st));
+    {
+      ProfScope ps(34, 2.0 * 3 * co * (double)HW * B, (double)B * HW * (sizeof(T) * co + 12 + (prev_rgb ? 3 : 0)), st);
+      SX_TRY(launch_torgb<T>(y2, styles + g->soffr[l], row, g->wrgb[l], prev_rgb, prev_bstride, rgb_dst, B, H, H, co, st));
+    }
     if (save_cache)
       SX_CUDA(cudaMemcpyAsync(cache_rgb(l), rgb_dst, (size_t)3 * HW * 4, cudaMemcpyDeviceToDevice, st));
     prev_rgb = rgb_dst;

@@ -179,6 +179,13 @@ int sx_attfind_select(const void* effects, int effects_f64, const float* base_lo
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics
  * ---------------------------------------------------------------------------------------------- */
+/* Per-kernel timing for bench.py's roofline: while enabled, every kernel of the generator plan is bracketed by
+ * CUDA events on its own stream.  sx_profile_collect synchronises those events and writes one row of 5 doubles
+ * per kernel kind: {kind, launches, total ms, algorithmic FLOPs, algorithmic bytes}; kinds 0..19 = conv index
+ * (2*block + {0,1}) of the plan, 32 modulate, 33 upsample+modulate, 34 ToRGB, 35 demod.  rows/n_rows: HOST. */
+int sx_profile_enable(int on);
+int sx_profile_collect(double* rows, int max_rows, int* n_rows);
+
 /* launches the tcgen05 kernel on a tiny problem and compares with the FFMA kernel; returns SX_OK when
  * max-abs error <= tol.  Host-synchronous.  max_err_out (host pointer) may be NULL. */
 int sx_tc_selftest(float tol, float* max_err_out);

@@ -213,8 +213,9 @@ def test_suffix_forward_equals_full_forward(dev, tc_ok, precision):
         full = plan.forward(rows, noise, precision=precision)
         # the full forward did not touch the cache (save_cache=False)
         suffix = plan.forward(rows, noise, start_conv=conv, precision=precision)
-        tol = 1e-5 if precision == "fp32" else 2e-2
-        assert (full - suffix).abs().max().item() <= tol, conv
+        # both paths feed bit-identical tensors to identical kernels (activations are rounded to the storage type
+        # before every modulation), so a zero shift gives an effect of exactly zero
+        assert torch.equal(full, suffix), (conv, (full - suffix).abs().max().item())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -308,7 +309,7 @@ def test_attfind_sweep_64px_subset_vs_oracle(dev, kind):
 
 def test_attfind_bf16_sweep_close_to_fp32(dev, tc_ok):
     _need_tc(tc_ok)
-    sd, G, lat, noise, clf_cpu, clf_gpu = _config64(dev, "resnet", 1)
+    sd, G, lat, noise, clf_cpu, clf_gpu = _config64(dev, "resnet", 3)
     S = G.num_style_coords
     sind = list(range(0, S, 61))
     r32 = sx.attfind_sweep(G, clf_gpu, lat.to(dev), noise.to(dev), precision="fp32", sindices=sind, max_batch=32)
@@ -316,7 +317,9 @@ def test_attfind_bf16_sweep_close_to_fp32(dev, tc_ok):
     err = (r32["style_change"] - r16["style_change"]).abs().max().item()
     mag = r32["style_change"].abs().max().item()
     print(f"bf16 vs fp32 effects: max err {err:.3e}, max|effect| {mag:.3e}")
-    assert err <= 0.1 * max(mag, 1e-2)
+    assert mag > 1e-2
+    # bf16 images differ from fp32 ones by <= 2e-2; the effects are differences of logits of such images
+    assert err <= max(0.25 * mag, 3e-2)
 
 
 def test_attfind_extraction_entry_point(dev, tmp_path):
