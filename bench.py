@@ -236,6 +236,27 @@ def run_ours(args):
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
 
+    class TimedClassifier:
+        """records CUDA events around every classifier call so the step breakdown can name the PyTorch share."""
+
+        def __init__(self, inner):
+            self.inner, self.events, self.on = inner, [], False
+
+        def classify_images(self, images):
+            if not self.on:
+                return self.inner.classify_images(images)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = self.inner.classify_images(images)
+            b.record()
+            self.events.append((a, b))
+            return out
+
+        def total_ms(self):
+            return sum(a.elapsed_time(b) for a, b in self.events)
+
+    clf = TimedClassifier(clf)
+
     # latent pool of the whole job; every rank derives the same minima/maxima from ALL of it (no collective)
     pool_n = args.pool * world
     lat_all = synthetic.make_latents(pool_n, 42)
@@ -267,6 +288,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     _native.profile_enable(True)
+    clf.on = True
     launches0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -281,6 +303,8 @@ def run_ours(args):
     launches = _native.launch_count() - launches0
     prof = _native.profile_collect()
     _native.profile_enable(False)
+    clf.on = False
+    clf_ms = clf.total_ms()
     clocks = sampler.stop()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     tot = torch.tensor([float(evals), float(launches)], device=dev, dtype=torch.float64)
@@ -356,6 +380,9 @@ def run_ours(args):
                         "frac": (bw_bytes / (bw_ms * 1e-3) / 1e9) / pk["hbm_gbs"] if bw_ms > 0 else None,
                         "share_of_step": bw_ms / ms if ms else None},
         "native_kernels_share_of_step": all_ms / ms if ms else None,
+        "classifier_share_of_step": clf_ms / ms if ms else None,
+        "kernel_ms_per_step": {{32: "modulate", 33: "upsample2x_modulate", 34: "torgb", 35: "demod"}.get(k, f"conv{k}"):
+                               round(v["ms"] / max(1, args.steps), 3) for k, v in sorted(prof.items())},
     }
 
     # ---------------- CPU baseline (reported only) ----------------

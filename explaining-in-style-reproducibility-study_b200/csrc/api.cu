@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_halo.cuh"
 #include "generator.cuh"
 
 using namespace sx;
@@ -114,7 +115,7 @@ int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, fl
     p.B = B; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.KS = k; p.ep = ep;
     return launch_conv_simt(p, st);
   }
-  return tc::launch_conv_tc(reinterpret_cast<__nv_bfloat16*>(ws + L.xmod), reinterpret_cast<__nv_bfloat16*>(ws + L.wpk), B, Ci, Co,
+  return tc::launch_conv_bf16(reinterpret_cast<__nv_bfloat16*>(ws + L.xmod), reinterpret_cast<__nv_bfloat16*>(ws + L.wpk), B, Ci, Co,
                             H, W, k, ep, st);
 }
 

@@ -13,29 +13,33 @@ namespace sx {
 // =================================================================================================
 
 // out[b, p, c] = in[b|0, p, c] * (style[b, c] + 1)          (style may be null: plain broadcast copy)
+// grid = (chunks of one sample, B): all index arithmetic is 32-bit (64-bit div/mod made the first version
+// of these kernels instruction-bound at 19 % of HBM peak).
 template <typename T>
 __global__ void __launch_bounds__(256) modulate_kernel(const T* __restrict__ in, long long in_bstride,
                                                        const float* __restrict__ style, int style_stride,
-                                                       T* __restrict__ out, int B, long long P, int C) {
+                                                       T* __restrict__ out, unsigned per_b /* P * C/V */, unsigned cv) {
   constexpr int V = Elem<T>::kVec;
   using vec_t = typename Elem<T>::vec_t;
-  const int cv = C / V;
-  const long long per_b = P * cv;
-  const long long total = (long long)B * per_b;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / per_b);
-    const long long r = i - (long long)b * per_b;
-    const int c = (int)(r % cv) * V;
-    vec_t v = *reinterpret_cast<const vec_t*>(in + (long long)b * in_bstride + r * V);
-    if (style) {
+  const unsigned b = blockIdx.y;
+  const vec_t* src = reinterpret_cast<const vec_t*>(in + (long long)b * in_bstride);
+  vec_t* dst = reinterpret_cast<vec_t*>(out) + (size_t)b * per_b;
+  const float* s = style ? style + (long long)b * style_stride : nullptr;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_b; i += gridDim.x * blockDim.x) {
+    vec_t v = __ldg(src + i);
+    if (s) {
+      const unsigned c = (i % cv) * V;
       float f[V];
       unpack(v, f);
-      const float* s = style + (long long)b * style_stride + c;
+      const float4* sp = reinterpret_cast<const float4*>(s + c);
 #pragma unroll
-      for (int j = 0; j < V; ++j) f[j] *= __ldg(s + j) + 1.f;
+      for (int j = 0; j < V / 4; ++j) {
+        const float4 m = __ldg(sp + j);
+        f[4 * j] *= m.x + 1.f; f[4 * j + 1] *= m.y + 1.f; f[4 * j + 2] *= m.z + 1.f; f[4 * j + 3] *= m.w + 1.f;
+      }
       pack(f, v);
     }
-    *reinterpret_cast<vec_t*>(out + i * V) = v;
+    dst[i] = v;
   }
 }
 
@@ -43,9 +47,12 @@ template <typename T>
 int launch_modulate(const T* in, long long in_bstride, const float* style, int style_stride, T* out, int B,
                     long long P, int C, cudaStream_t st) {
   SX_REQUIRE(C % Elem<T>::kVec == 0, "modulate: C=%d not a multiple of %d", C, Elem<T>::kVec);
-  const long long total = (long long)B * P * (C / Elem<T>::kVec);
-  if (total == 0) return SX_OK;
-  modulate_kernel<T><<<ew_grid(total, 256), 256, 0, st>>>(in, in_bstride, style, style_stride, out, B, P, C);
+  const long long per_b = P * (C / Elem<T>::kVec);
+  SX_REQUIRE(per_b < (1ll << 31), "modulate: sample too large");
+  if (per_b == 0 || B == 0) return SX_OK;
+  const int gx = (int)((per_b + 255) / 256 < 4 * num_sms() ? (per_b + 255) / 256 : 4 * num_sms());
+  dim3 grid(gx, B);
+  modulate_kernel<T><<<grid, 256, 0, st>>>(in, in_bstride, style, style_stride, out, (unsigned)per_b, (unsigned)(C / Elem<T>::kVec));
   SX_CHECK_LAUNCH();
   return SX_OK;
 }
@@ -60,45 +67,51 @@ __device__ __forceinline__ void bilinear_src(int o, int n_in, int& i0, int& i1, 
   l0 = 1.f - l1;
 }
 
+constexpr int UPS_ROWS = 8;  // output rows per CTA of the upsample kernel
+
 // out[b, 2H, 2W, C] = upsample2x(in[b|0]) * (style[b, c] + 1)      (ST:679,693-694 fused with the
-// activation-side modulation of the next conv1).  H, W are the INPUT sizes.
+// activation-side modulation of the next conv1).  H, W are the INPUT sizes.  grid = (row chunks, 2H, B).
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_modulate_kernel(const T* __restrict__ in, long long in_bstride,
                                                                   const float* __restrict__ style, int style_stride,
-                                                                  T* __restrict__ out, int B, int H, int W, int C) {
+                                                                  T* __restrict__ out, int H, int W, int C) {
   constexpr int V = Elem<T>::kVec;
   using vec_t = typename Elem<T>::vec_t;
-  const int cv = C / V;
-  const int OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)B * OH * OW * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * V;
-    long long r = i / cv;
-    const int ox = (int)(r % OW);
-    r /= OW;
-    const int oy = (int)(r % OH);
-    const int b = (int)(r / OH);
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
-    bilinear_src(oy, H, y0, y1, ly0, ly1);
-    bilinear_src(ox, W, x0, x1, lx0, lx1);
-    const T* src = in + (long long)b * in_bstride + c;
+  const unsigned cv = C / V;
+  const int OW = 2 * W;
+  const int b = blockIdx.z;
+  const T* src = in + (long long)b * in_bstride;
+  const float* s = style ? style + (long long)b * style_stride : nullptr;
+  const unsigned row = OW * cv;
+  for (int oy = blockIdx.y * UPS_ROWS; oy < (int)(blockIdx.y + 1) * UPS_ROWS && oy < 2 * H; ++oy) {
+  int y0, y1;
+  float ly0, ly1;
+  bilinear_src(oy, H, y0, y1, ly0, ly1);
+  const T* r0 = src + (size_t)y0 * W * C;
+  const T* r1 = src + (size_t)y1 * W * C;
+  T* dst = out + ((size_t)b * 2 * H + oy) * OW * C;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < row; i += gridDim.x * blockDim.x) {
+    const unsigned ox = i / cv;
+    const unsigned c = (i - ox * cv) * V;
+    int x0, x1;
+    float lx0, lx1;
+    bilinear_src((int)ox, W, x0, x1, lx0, lx1);
     float f00[V], f01[V], f10[V], f11[V], o[V];
-    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y0 * W + x0) * C), f00);
-    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y0 * W + x1) * C), f01);
-    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y1 * W + x0) * C), f10);
-    unpack(*reinterpret_cast<const vec_t*>(src + ((long long)y1 * W + x1) * C), f11);
+    unpack(__ldg(reinterpret_cast<const vec_t*>(r0 + (size_t)x0 * C + c)), f00);
+    unpack(__ldg(reinterpret_cast<const vec_t*>(r0 + (size_t)x1 * C + c)), f01);
+    unpack(__ldg(reinterpret_cast<const vec_t*>(r1 + (size_t)x0 * C + c)), f10);
+    unpack(__ldg(reinterpret_cast<const vec_t*>(r1 + (size_t)x1 * C + c)), f11);
 #pragma unroll
     for (int j = 0; j < V; ++j) o[j] = ly0 * (lx0 * f00[j] + lx1 * f01[j]) + ly1 * (lx0 * f10[j] + lx1 * f11[j]);
-    if (style) {
+    if (s) {
       // round to the storage type first: identical to upsample -> cache -> modulate of the AttFind suffix path
-      const float* s = style + (long long)b * style_stride + c;
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = to_f(from_f<T>(o[j])) * (__ldg(s + j) + 1.f);
+      for (int j = 0; j < V; ++j) o[j] = to_f(from_f<T>(o[j])) * (__ldg(s + c + j) + 1.f);
     }
     vec_t v;
     pack(o, v);
-    *reinterpret_cast<vec_t*>(out + i * V) = v;
+    *reinterpret_cast<vec_t*>(dst + (size_t)i * V) = v;
+  }
   }
 }
 
@@ -106,9 +119,12 @@ template <typename T>
 int launch_upsample2x_modulate(const T* in, long long in_bstride, const float* style, int style_stride, T* out, int B,
                                int H, int W, int C, cudaStream_t st) {
   SX_REQUIRE(C % Elem<T>::kVec == 0, "upsample: C=%d not a multiple of %d", C, Elem<T>::kVec);
-  const long long total = (long long)B * 4 * H * W * (C / Elem<T>::kVec);
-  if (total == 0) return SX_OK;
-  upsample2x_modulate_kernel<T><<<ew_grid(total, 256), 256, 0, st>>>(in, in_bstride, style, style_stride, out, B, H, W, C);
+  if (B == 0) return SX_OK;
+  const int row = 2 * W * (C / Elem<T>::kVec);
+  const int threads = row >= 256 ? 256 : (row >= 128 ? 128 : 64);
+  dim3 grid((row + threads - 1) / threads, (2 * H + UPS_ROWS - 1) / UPS_ROWS, B);
+  SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "upsample: grid too large");
+  upsample2x_modulate_kernel<T><<<grid, threads, 0, st>>>(in, in_bstride, style, style_stride, out, H, W, C);
   SX_CHECK_LAUNCH();
   return SX_OK;
 }
@@ -148,28 +164,59 @@ __device__ __forceinline__ float up2_blur(const float* __restrict__ p, const flo
 // RGBBlock (ST:618-629) for one block, fused with the previous block's Upsample+Blur tail:
 //   rgb[b, c, y, x] = sum_o y2[b, y, x, o] * (sr[b, o] + 1) * Wrgb[c, o]  +  blur(up2x(prev[b|0]))[c, y, x]
 // y2 NHWC (T), prev [Bp, 3, H/2, W/2] fp32 planar (null for the first block), rgb [B,3,H,W] fp32 planar.
-// One thread per pixel; the 3 x Co modulated weights of the sample sit in shared memory.
+// One CTA = one (<=16 x 16)-pixel tile of one sample:
+//   phase A  the (TH+2) x (TW+2) window of upsample2x(prev) the blur needs (reflect border) goes to shared memory
+//            once per tile (~4 bilinear samples per thread instead of 108 per pixel), then a 9-tap blur from smem;
+//   phase B  the 1x1 conv with LPP = min(32, Co/V) lanes per pixel: every lane loads 16 B of consecutive channels, so
+//            a warp load instruction reads whole contiguous pixel rows (coalesced), partial sums are shuffle-reduced;
+//   phase C  planar fp32 stores, 16 consecutive x per row.
 template <typename T>
 __global__ void __launch_bounds__(256) torgb_kernel(const T* __restrict__ y2, const float* __restrict__ rgb_style,
                                                     int style_stride, const float* __restrict__ wrgb,
                                                     const float* __restrict__ prev, long long prev_bstride,
-                                                    float* __restrict__ rgb, int H, int W, int Co) {
-  extern __shared__ float s_w[];  // [3][Co]
+                                                    float* __restrict__ rgb, int H, int W, int Co, int TH, int TW) {
+  extern __shared__ float smem_f[];
   constexpr int V = Elem<T>::kVec;
   using vec_t = typename Elem<T>::vec_t;
+  float* s_w = smem_f;                        // [3][Co]
+  float* s_res = s_w + 3 * Co;                // [3][256]
+  float* s_up = s_res + 3 * 256;              // [3][(TH+2)*(TW+2)]
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 3 * Co; i += blockDim.x) {
+  const int tiles_x = W / TW;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  const int npix = TH * TW;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 3 * Co; i += blockDim.x) {
     const int o = i % Co;
     s_w[i] = (__ldg(rgb_style + (long long)b * style_stride + o) + 1.f) * __ldg(wrgb + i);
   }
+  const int UW = TW + 2, UH = TH + 2;
+  if (prev) {
+    const float* pp = prev + (long long)b * prev_bstride;
+    const int h = H / 2, w = W / 2;
+    for (int i = tid; i < 3 * UH * UW; i += blockDim.x) {
+      const int c = i / (UH * UW);
+      const int r = i - c * UH * UW;
+      const int uy = r / UW, ux = r - uy * UW;
+      s_up[i] = up2(pp + c * h * w, nullptr, h, w, reflect1(y0 - 1 + uy, H), reflect1(x0 - 1 + ux, W));
+    }
+  }
   __syncthreads();
-  const int HW = H * W;
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
-    const T* src = y2 + ((long long)b * HW + pix) * Co;
+  // ---- phase B
+  const int lpp = Co / V < 32 ? Co / V : 32;         // lanes per pixel (power of two: Co is 32..512, V 4|8)
+  const int ppw = 32 / lpp;                           // pixels per warp iteration
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int sub = lane / lpp, cl = lane - sub * lpp;  // pixel slot in the warp, channel lane
+  for (int p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
+    const int pl = p0 + sub;                          // pixel index in the tile
+    const bool live = pl < npix;
+    const int py = pl / TW, px = pl - py * TW;
+    const T* src = y2 + (((long long)b * H + y0 + py) * W + x0 + px) * Co;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int o = 0; o < Co; o += V) {
+    for (int o = cl * V; live && o < Co; o += lpp * V) {
       float f[V];
-      unpack(*reinterpret_cast<const vec_t*>(src + o), f);
+      unpack(__ldg(reinterpret_cast<const vec_t*>(src + o)), f);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         a0 = fmaf(f[j], s_w[o + j], a0);
@@ -177,32 +224,51 @@ __global__ void __launch_bounds__(256) torgb_kernel(const T* __restrict__ y2, co
         a2 = fmaf(f[j], s_w[2 * Co + o + j], a2);
       }
     }
-    const int y = pix / W, x = pix - y * W;
-    if (prev) {
-      const float* pp = prev + (long long)b * prev_bstride;
-      const int h = H / 2, w = W / 2;
-      a0 += up2_blur(pp, nullptr, h, w, y, x);
-      a1 += up2_blur(pp + h * w, nullptr, h, w, y, x);
-      a2 += up2_blur(pp + 2 * h * w, nullptr, h, w, y, x);
+    for (int off = lpp >> 1; off > 0; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
     }
-    float* dst = rgb + (long long)b * 3 * HW + pix;
-    dst[0] = a0;
-    dst[HW] = a1;
-    dst[2 * HW] = a2;
+    if (cl == 0 && live) {
+      s_res[pl] = a0;
+      s_res[256 + pl] = a1;
+      s_res[512 + pl] = a2;
+    }
+  }
+  __syncthreads();
+  // ---- phase C
+  const long long HW = (long long)H * W;
+  for (int pl = tid; pl < npix; pl += blockDim.x) {
+    const int py = pl / TW, px = pl - py * TW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = s_res[c * 256 + pl];
+      if (prev) {
+        const float* u = s_up + c * UH * UW + py * UW + px;   // window origin = (y0-1, x0-1)
+        v += (1.f / 16.f) * (u[0] + u[2] + u[2 * UW] + u[2 * UW + 2]) + (2.f / 16.f) * (u[1] + u[UW] + u[UW + 2] + u[2 * UW + 1]) +
+             (4.f / 16.f) * u[UW + 1];
+      }
+      rgb[((long long)b * 3 + c) * HW + (long long)(y0 + py) * W + x0 + px] = v;
+    }
   }
 }
 
 template <typename T>
 int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const float* wrgb, const float* prev,
                  long long prev_bstride, float* rgb, int B, int H, int W, int Co, cudaStream_t st) {
-  SX_REQUIRE(Co % Elem<T>::kVec == 0, "torgb: Co=%d not a multiple of %d", Co, Elem<T>::kVec);
+  constexpr int V = Elem<T>::kVec;
+  SX_REQUIRE(Co % V == 0, "torgb: Co=%d not a multiple of %d", Co, V);
+  const int lpp = Co / V < 32 ? Co / V : 32;
+  SX_REQUIRE((lpp & (lpp - 1)) == 0, "torgb: Co/%d = %d must be a power of two (or >= 32)", V, Co / V);
+  SX_REQUIRE(Co / V < 32 || Co % (32 * V) == 0, "torgb: Co=%d must be a multiple of %d", Co, 32 * V);
   if (B == 0) return SX_OK;
-  const int HW = H * W;
-  const int threads = HW >= 256 ? 256 : 64;
-  int gx = (HW + threads - 1) / threads;
-  dim3 grid(gx, B);
-  torgb_kernel<T><<<grid, threads, 3 * Co * sizeof(float), st>>>(y2, rgb_style, style_stride, wrgb, prev, prev_bstride,
-                                                              rgb, H, W, Co);
+  const int TW = W < 16 ? W : 16, TH = H < 16 ? H : 16;
+  SX_REQUIRE(W % TW == 0 && H % TH == 0, "torgb: H, W must be multiples of the tile");
+  const int npix = TH * TW;
+  const int threads = npix >= 256 ? 256 : (npix >= 64 ? 64 : 32);
+  dim3 grid((W / TW) * (H / TH), B);
+  const size_t smem = (size_t)(3 * Co + 3 * 256 + 3 * (TH + 2) * (TW + 2)) * sizeof(float);
+  torgb_kernel<T><<<grid, threads, smem, st>>>(y2, rgb_style, style_stride, wrgb, prev, prev_bstride, rgb, H, W, Co, TH, TW);
   SX_CHECK_LAUNCH();
   return SX_OK;
 }

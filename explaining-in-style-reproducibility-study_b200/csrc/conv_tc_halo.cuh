@@ -1,0 +1,371 @@
+// conv_tc_halo.cuh -- persistent, halo-reusing variant of the tcgen05 3x3 convolution for the high-resolution,
+// narrow layers (Co <= 128, H >= 16) where conv_tc_kernel is bound by L2->shared-memory traffic: it re-loads the
+// 128-pixel activation tile once per tap (9x).  Here a CTA tile is 16 rows x 8 pixels; ONE TMA box of 18 x 10
+// pixels (the tile plus its 1-pixel halo; out-of-bounds = zero = the conv padding) is loaded per 64-channel chunk
+// and all 9 taps read it in place:
+//
+//   smem row of halo pixel (hy, hx)        = hy * 10 + hx                     (rows of BLOCK_K bf16, TMA-swizzled)
+//   A operand of tap (ky, kx)              = rows (yy + ky) * 10 + (xx + kx),  yy < 16, xx < 8
+//                                          = 16 groups of 8 consecutive rows, groups 10 rows apart
+//   => UMMA smem descriptor: start = base + (ky*10 + kx) * row_bytes,  SBO = 10 * row_bytes
+//
+// The start address is then only row-aligned (not 1024 B aligned).  That is legal because the 128B/64B swizzle of
+// both TMA and tcgen05.mma is a function of the shared-memory ADDRESS bits (XOR of bits [4,7) with bits [7,10)) --
+// the same property the K-advance of +32 B inside a swizzled row relies on (conv_tc.cuh, verified on hardware).
+//
+// Persistent: grid = resident CTAs; each CTA walks tiles t = blockIdx.x + i * gridDim.x.  Two TMEM accumulators
+// (2 x BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1; the TMA producer runs ahead
+// across tile boundaries.  For the last block(s) the whole 9-tap weight set of the layer (<= 72 KB) stays
+// RESIDENT in shared memory for the CTA's lifetime; otherwise weights stream through their own ring.
+#pragma once
+
+#include "conv_tc.cuh"
+
+namespace sx {
+namespace tc {
+
+constexpr int HALO_BW = 8, HALO_BH = 16, HALO_W = HALO_BW + 2, HALO_H = HALO_BH + 2, HALO_ROWS = HALO_W * HALO_H;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// like make_smem_desc but with an explicit stride between 8-row groups
+template <int BLOCK_K>
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  constexpr uint64_t layout = BLOCK_K * 2 == 128 ? 2 : 4;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
+struct HaloCfg {
+  static constexpr int kRowBytes = BLOCK_K * 2;
+  static constexpr int kATx = HALO_ROWS * kRowBytes;              // bytes one halo box delivers
+  static constexpr int kABytes = (kATx + 1023) / 1024 * 1024;     // stage stride (keeps every stage 1024 B aligned)
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;           // weights of one (channel chunk, tap)
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
+  __host__ __device__ static size_t b_region(int num_b_tiles) { return (size_t)(RESIDENT_B ? num_b_tiles : B_STAGES) * kBBytes; }
+  static size_t smem_bytes(int num_b_tiles) {
+    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + 256 + (size_t)(2 + 4) * BLOCK_N * sizeof(float);
+  }
+};
+
+struct ConvHaloParams {
+  int B, H, W, Ci, Co;
+  int tiles_x, tiles_y, num_tiles;   // W/8, H/16, B*tiles_y*tiles_x
+  int kchunks, num_b_tiles;          // Ci/BLOCK_K, 9*kchunks
+  ConvEpilogue ep;
+};
+
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
+__global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                   const __grid_constant__ CUtensorMap tmap_b,
+                                                                   const ConvHaloParams p) {
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_STAGES * Cfg::kABytes;
+  uint8_t* after = smem_b + Cfg::b_region(p.num_b_tiles);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(after);
+  uint64_t* a_empty = a_full + A_STAGES;
+  uint64_t* b_full = a_empty + A_STAGES;          // [B_STAGES]  (resident: b_full[0] = "all weights landed")
+  uint64_t* b_empty = b_full + B_STAGES;
+  uint64_t* tmem_full = b_empty + B_STAGES;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  static_assert((2 * A_STAGES + 2 * B_STAGES + 4) * 8 + 8 <= 256, "barrier block overflow");
+  float* s_nw = reinterpret_cast<float*>(after + 256);
+  float* s_nb = s_nw + BLOCK_N;
+  float* s_d = s_nb + BLOCK_N;            // [2][BLOCK_N] demod coefficients of the tile's sample (per accumulator slot)
+  float* s_m = s_d + 2 * BLOCK_N;         // [2][BLOCK_N] next-layer (style+1)
+
+  const int warp_id = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int tiles_per_b = p.tiles_x * p.tiles_y;
+
+  if (warp_id == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    fence_barrier_init();
+  } else if (warp_id == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_id == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (RESIDENT_B) {
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(p.num_b_tiles * Cfg::kBBytes));
+        for (int i = 0; i < p.num_b_tiles; ++i) {
+          const int chunk = i / 9, tap = i - chunk * 9;
+          tma_load_2d(smem_b + (size_t)i * Cfg::kBBytes, &tmap_b, &b_full[0], tap * p.Ci + chunk * BLOCK_K, n0);
+        }
+      }
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_b;
+        const int tr = tile - b * tiles_per_b;
+        const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+        const int x0 = tx * HALO_BW, y0 = ty * HALO_BH;
+        for (int chunk = 0; chunk < p.kchunks; ++chunk) {
+          mbar_wait(&a_empty[as], aph ^ 1, 10);
+          mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
+          tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (!RESIDENT_B) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1, 11);
+              mbar_arrive_expect_tx(&b_full[bs], Cfg::kBBytes);
+              tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmap_b, &b_full[bs], tap * p.Ci + chunk * BLOCK_K, n0);
+              if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_id == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      constexpr uint32_t sbo = HALO_W * Cfg::kRowBytes;
+      if (RESIDENT_B) {
+        mbar_wait(&b_full[0], 0, 12);
+        tc_fence_after();
+      }
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, accph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int chunk = 0; chunk < p.kchunks; ++chunk) {
+          mbar_wait(&a_full[as], aph, 14);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem_a + as * Cfg::kABytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t b_addr;
+            if (RESIDENT_B) {
+              b_addr = smem_u32(smem_b + (size_t)(chunk * 9 + tap) * Cfg::kBBytes);
+            } else {
+              mbar_wait(&b_full[bs], bph, 15);
+              tc_fence_after();
+              b_addr = smem_u32(smem_b + bs * Cfg::kBBytes);
+            }
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint64_t da = make_smem_desc_sbo<BLOCK_K>(a_base + (uint32_t)((ky * HALO_W + kx) * Cfg::kRowBytes), sbo);
+            const uint64_t db = make_smem_desc<BLOCK_K>(b_addr);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+            if (!RESIDENT_B) {
+              umma_commit(&b_empty[bs]);
+              if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) accph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const ConvEpilogue& ep = p.ep;
+    const int et = threadIdx.x - 64;  // 0..127
+    for (int i = et; i < BLOCK_N; i += 128) {
+      s_nw[i] = ep.noise ? __ldg(ep.noise_w + n0 + i) : 0.f;
+      s_nb[i] = ep.noise ? __ldg(ep.noise_b + n0 + i) : 0.f;
+    }
+    const int q = warp_id & 3;          // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;        // tile row = TMEM lane
+    const int yy = r >> 3, xx = r & 7;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_b;
+      const int tr = tile - b * tiles_per_b;
+      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      const int x = tx * HALO_BW + xx, y = ty * HALO_BH + yy;
+      float* dd = s_d + acc * BLOCK_N;
+      float* mm = s_m + acc * BLOCK_N;
+      for (int i = et; i < BLOCK_N; i += 128) {
+        dd[i] = ep.dcoef ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + i) : 1.f;
+        mm[i] = ep.next_style ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) + 1.f : 1.f;
+      }
+      float nz = 0.f;
+      if (ep.noise) {
+        const int S = ep.noise_size;
+        nz = __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
+      }
+      const long long pix = ((long long)b * p.H + y) * p.W + x;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // tables of this tile visible to all epilogue warps
+      mbar_wait(&tmem_full[acc], accph, 16);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+        tmem_ld_wait();
+        float f[32], fr[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(v[j]) * dd[c0 + j];
+          t += nz * s_nw[c0 + j] + s_nb[c0 + j];
+          if (ep.act) t = lrelu02(t);
+          if (!ep.out_nchw_f32) t = __bfloat162float(__float2bfloat16_rn(t));  // see conv_tc.cuh: round before modulating
+          fr[j] = t;
+          f[j] = t * mm[c0 + j];
+        }
+        if (ep.out_nchw_f32) {
+          float* out = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
+        } else {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pack(f + j, pk);
+            *reinterpret_cast<uint4*>(out + j) = pk;
+          }
+        }
+        if (ep.out_raw) {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pack(fr + j, pk);
+            *reinterpret_cast<uint4*>(out + j) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);   // 128 arrivals release the accumulator to the MMA warp
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+inline bool halo_shape_supported(int Ci, int Co, int H, int W) {
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  if (!(Co == 32 || Co == 64 || Co == 128)) return false;
+  if (Ci % 32 != 0) return false;
+  if (H != W || !pow2(W) || H < HALO_BH) return false;
+  return true;
+}
+
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
+int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(SX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const CUtensorMapSwizzle swz = BLOCK_K == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)p.Ci, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)p.W * p.Ci * 2, (cuuint64_t)p.H * p.W * p.Ci * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)9 * p.Ci;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)p.Co};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_N};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wk), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
+  const size_t smem = Cfg::smem_bytes(p.num_b_tiles);
+  if (smem > 227 * 1024) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %zu bytes of shared memory needed", smem);
+  static size_t configured = 0;
+  static int occ_cached = 0;
+  if (smem > configured) {
+    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+    occ_cached = 0;
+  }
+  if (occ_cached == 0) {
+    int occ = 0;
+    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NUM_THREADS, smem));
+    const int tmem_limit = 512 / Cfg::kTmemCols;   // resident CTAs must all fit their TMEM allocation
+    occ = occ < tmem_limit ? occ : tmem_limit;
+    occ_cached = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
+  }
+  int grid_x = occ_cached * num_sms();
+  if (grid_x > p.num_tiles) grid_x = p.num_tiles;
+  dim3 grid((unsigned)grid_x, (unsigned)(p.Co / BLOCK_N));
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, p);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+// returns SX_EUNSUPPORTED (without setting an error the caller must report) when the halo kernel does not cover the shape
+inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int B, int Ci, int Co, int H, int W,
+                            const ConvEpilogue& ep, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (!halo_shape_supported(Ci, Co, H, W) || B == 0) return SX_OK;
+  const int bk = Ci % 64 == 0 ? 64 : 32;
+  ConvHaloParams p;
+  p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
+  p.tiles_x = W / HALO_BW; p.tiles_y = H / HALO_BH;
+  p.num_tiles = B * p.tiles_x * p.tiles_y;
+  p.kchunks = Ci / bk;
+  p.num_b_tiles = 9 * p.kchunks;
+  p.ep = ep;
+  const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
+  const bool resident = weight_bytes <= 80 * 1024;
+  *handled = true;
+  if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 3, 2, true>(x, wk, p, stream);
+  if (Co == 32 && bk == 32 && resident) return launch_conv_halo_cfg<32, 32, 3, 2, true>(x, wk, p, stream);
+  if (Co == 64 && bk == 64 && resident) return launch_conv_halo_cfg<64, 64, 3, 2, true>(x, wk, p, stream);
+  if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 3, 6, false>(x, wk, p, stream);
+  if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 3, 4, false>(x, wk, p, stream);
+  *handled = false;
+  return SX_OK;
+}
+
+// bf16 Conv2DMod dispatch: the halo-reusing persistent kernel where it applies, the per-tap kernel otherwise.
+// SX_DISABLE_HALO=1 forces the per-tap kernel (A/B measurements).
+inline int launch_conv_bf16(const __nv_bfloat16* x, const __nv_bfloat16* wk, int B, int Ci, int Co, int H, int W, int KS,
+                            const ConvEpilogue& ep, cudaStream_t stream) {
+  static const bool halo_off = getenv("SX_DISABLE_HALO") != nullptr;
+  if (!halo_off && KS == 3) {
+    bool handled = false;
+    SX_TRY(launch_conv_halo(x, wk, B, Ci, Co, H, W, ep, stream, &handled));
+    if (handled) return SX_OK;
+  }
+  return launch_conv_tc(x, wk, B, Ci, Co, H, W, KS, ep, stream);
+}
+
+}  // namespace tc
+}  // namespace sx

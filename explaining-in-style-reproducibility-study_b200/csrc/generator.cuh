@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_halo.cuh"
 
 struct sx_generator {
   int num_blocks = 0, latent = 0, image_size = 0;
@@ -202,7 +203,7 @@ template <>
 inline int run_conv<__nv_bfloat16>(const sx_generator* g, int conv_idx, const __nv_bfloat16* x, int B, int Ci, int Co, int H,
                                    const ConvEpilogue& ep, cudaStream_t st) {
   ProfScope ps(conv_idx, 2.0 * 9 * Ci * Co * (double)H * H * B, 2.0 * B * H * H * (Ci + Co), st);
-  return tc::launch_conv_tc(x, g->conv[conv_idx].wbf, B, Ci, Co, H, H, 3, ep, st);
+  return tc::launch_conv_bf16(x, g->conv[conv_idx].wbf, B, Ci, Co, H, H, 3, ep, st);
 }
 
 template <typename T>

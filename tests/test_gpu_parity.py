@@ -86,7 +86,8 @@ def test_tcgen05_selftest(tc_ok):
 
 
 @pytest.mark.parametrize("B,Ci,Co,H", [(2, 64, 64, 16), (3, 32, 32, 8), (1, 64, 32, 64), (2, 512, 512, 4), (9, 256, 128, 4),
-                                        (1, 128, 64, 128), (2, 64, 32, 256)])
+                                        (1, 128, 64, 128), (2, 64, 32, 256), (2, 32, 32, 64), (1, 256, 128, 32),
+                                        (3, 128, 128, 16), (1, 512, 256, 32), (5, 32, 32, 16)])
 def test_conv2dmod_bf16(dev, tc_ok, B, Ci, Co, H):
     _need_tc(tc_ok)
     g = torch.Generator().manual_seed(B * 1000 + Ci + Co + H)
@@ -320,6 +321,54 @@ def test_attfind_bf16_sweep_close_to_fp32(dev, tc_ok):
     assert mag > 1e-2
     # bf16 images differ from fp32 ones by <= 2e-2; the effects are differences of logits of such images
     assert err <= max(0.25 * mag, 3e-2)
+
+
+@pytest.mark.parametrize("size,precision", [(64, "fp32"), (256, "bf16")])
+def test_sweep_properties_at_baseline_sizes(dev, tc_ok, size, precision):
+    """size-independent properties at the BASELINE generator shapes (no oracle needed):
+    (1) shift_size = 0 => every effect is EXACTLY 0 (suffix path == clean path bit for bit, drift-free);
+    (2) sharding invariance: sweeping with (rank, world) = (0,2),(1,2) and concatenating == the single-rank sweep;
+    (3) a coordinate already at its minimum / maximum gives an exactly-zero effect in that direction."""
+    if precision == "bf16":
+        _need_tc(tc_ok)
+    sd = synthetic.make_generator_state(size, seed=42)
+    G = g_module(sd, size, 16, dev)
+    lat = synthetic.make_latents(2, 42).to(dev)
+    noise = synthetic.make_noise(size, 42).to(dev)
+    torch.manual_seed(0)
+    # batch-size independent classifier (no cuDNN algorithm choice): the property is about OUR path
+    coef = torch.randn(2, 16).tolist()
+
+    class Pool:
+        """logits = fixed linear readout of 16 pixels, accumulated with elementwise ops only: bit-identical for
+        every batch size, so any non-zero effect can only come from the generator path under test."""
+
+        def classify_images(self, x):
+            f = x[:, :, 1::(size // 3), 2::(size // 3)].reshape(x.shape[0], -1)
+            out = []
+            for c in range(2):
+                acc = f[:, 0] * coef[c][0]
+                for j in range(1, 16):
+                    acc = acc + f[:, j] * coef[c][j]
+                out.append(acc)
+            return torch.stack(out, dim=1)
+    S = G.num_style_coords
+    sind = sorted(set(range(0, S, max(1, S // 40))) | {S - 1})
+    r0 = sx.attfind_sweep(G, Pool(), lat, noise, shift_size=0.0, precision=precision, sindices=sind, max_batch=16)
+    assert float(r0["style_change"].abs().max()) == 0.0
+    full = sx.attfind_sweep(G, Pool(), lat, noise, precision=precision, sindices=sind, max_batch=16)
+    parts = [sx.attfind_sweep(G, Pool(), lat, noise, precision=precision, sindices=sind, max_batch=16, rank=r, world_size=2,
+                              gather=False)["style_change"] for r in range(2)]
+    assert torch.equal(torch.cat(parts), full["style_change"])
+    sc, mn, mx = full["style_coordinates"], full["minima"], full["maxima"]
+    eff = full["style_change"]
+    for n in range(2):
+        for s in sind:
+            if sc[n, s] == mn[s]:
+                assert float(eff[n, 0, s].abs().max()) == 0.0
+            if sc[n, s] == mx[s]:
+                assert float(eff[n, 1, s].abs().max()) == 0.0
+    assert float(eff.abs().max()) > 0
 
 
 def test_attfind_extraction_entry_point(dev, tmp_path):
