@@ -49,10 +49,12 @@ def parse():
     ap.add_argument("--classifier", default="resnet", choices=["resnet", "mobilenet"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--classifier-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--classifier-mode", default="fused", choices=["fused", "eager"],
+                    help="fused: BatchNorm folded + PyTorch's fused cuDNN conv+bias+ReLU ops; eager: the module as is")
     ap.add_argument("--latents-per-step", type=int, default=1)
     ap.add_argument("--pool", type=int, default=16, help="latents per rank prepared up front (minima/maxima pool)")
     ap.add_argument("--max-batch", type=int, default=128)
-    ap.add_argument("--cpu-sample-coords", type=int, default=24, help="style coordinates in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample-coords", type=int, default=160, help="style coordinates in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -236,6 +238,22 @@ def run_ours(args):
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
 
+    clf_mode = "eager"
+    if args.classifier_mode == "fused" and kind == "resnet":
+        try:  # validate the fused forward against the eager module on real generated images before trusting it
+            probe = calib[:8]
+            ref_logits = clf.classify_images(probe)
+            clf.fuse_for_inference()
+            got = clf.classify_images(probe)
+            torch.cuda.synchronize()
+            tol = 0.05 * float(ref_logits.abs().max()) + 0.05
+            if not torch.isfinite(got).all() or float((got - ref_logits).abs().max()) > tol:
+                raise RuntimeError(f"fused classifier deviates: {float((got - ref_logits).abs().max()):.3e} > {tol:.3e}")
+            clf_mode = "fused (BN folded, aten::cudnn_convolution_[add_]relu)"
+        except Exception as e:  # noqa: BLE001 -- any failure means: keep the eager module, say so in the JSON
+            clf.fused = None
+            clf_mode = f"eager (fused path unavailable: {type(e).__name__}: {str(e)[:120]})"
+
     class TimedClassifier:
         """records CUDA events around every classifier call so the step breakdown can name the PyTorch share."""
 
@@ -403,7 +421,7 @@ def run_ours(args):
         "config": {"workload": f"StylEx {size}px FFHQ-shaped generator (capacity 16, S={S}) + {kind}-18@224 classifier; "
                                f"AttFind sweep, {lps} latent(s)/rank/step x {S} coords x 2 directions",
                    "coord_evals_per_step": int(2 * S * lps * world), "max_batch": args.max_batch,
-                   "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)",
+                   "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)", "classifier_mode": clf_mode,
                    "prefix_reuse": True, "l2": "inputs larger than L2: every 128-eval batch streams >2 GB of activations (L2 = 126 MB)",
                    "pool_latents": pool_n, "parallelism": f"latent-sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roofline, "cpu_baseline": cpu,

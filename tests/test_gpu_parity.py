@@ -402,6 +402,22 @@ def test_attfind_extraction_entry_point(dev, tmp_path):
         sx.attfind_extraction(images, 3, None, st, clf, None, noise, 2464, 1, -0.5, image_size=size)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
+def test_fused_classifier_matches_eager(dev, dtype, tol):
+    """the opt-in fused ResNet inference path (folded BN + PyTorch's fused cuDNN ops) is the same function."""
+    model = synthetic.make_classifier_model("resnet", 3)
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(16, 3, 64, 64, generator=g) * 2 - 0.5
+    clf = sx.make_classifier("resnet", model, 64)
+    synthetic.calibrate_classifier(model, clf.preprocess, imgs, chunk=8)
+    clf.to(dev).set_compute(dtype, channels_last=True)
+    ref = clf.classify_images(imgs.to(dev))
+    clf.fuse_for_inference()
+    got = clf.classify_images(imgs.to(dev))
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
 def test_native_launches_counted(dev):
     before = _native.launch_count()
     sx.modules.upsample2x(torch.zeros(1, 1, 4, 4, device=dev))
