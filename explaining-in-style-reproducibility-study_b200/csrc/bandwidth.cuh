@@ -67,10 +67,26 @@ __device__ __forceinline__ void bilinear_src(int o, int n_in, int& i0, int& i1, 
   l0 = 1.f - l1;
 }
 
-constexpr int UPS_ROWS = 8;  // output rows per CTA of the upsample kernel
+constexpr int UPS_ROWS = 4;  // INPUT rows per CTA of the upsample kernel (8 output rows)
 
 // out[b, 2H, 2W, C] = upsample2x(in[b|0]) * (style[b, c] + 1)      (ST:679,693-694 fused with the
-// activation-side modulation of the next conv1).  H, W are the INPUT sizes.  grid = (row chunks, 2H, B).
+// activation-side modulation of the next conv1).  H, W are the INPUT sizes.
+// One thread = one 2x2 output quad x V channels.  Interior quads read their 3x3 input neighbourhood once (9 vector
+// loads for 4 outputs) and use the constant bilinear weights (0.25, 0.75) in torch's evaluation order; border quads
+// (clamped source indices) take the generic per-pixel path.  The first version (1 output per thread, 4 loads, per-pixel
+// weight computation) was instruction-bound at 28 % of the HBM roofline.
+template <typename T>
+__device__ __forceinline__ void ups_store(T* __restrict__ dst, const float* __restrict__ o, const float* __restrict__ m, bool mod) {
+  constexpr int V = Elem<T>::kVec;
+  using vec_t = typename Elem<T>::vec_t;
+  float r[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) r[k] = mod ? to_f(from_f<T>(o[k])) * m[k] : o[k];   // round to storage type, then modulate
+  vec_t v;
+  pack(r, v);
+  *reinterpret_cast<vec_t*>(dst) = v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_modulate_kernel(const T* __restrict__ in, long long in_bstride,
                                                                   const float* __restrict__ style, int style_stride,
@@ -82,36 +98,83 @@ __global__ void __launch_bounds__(256) upsample2x_modulate_kernel(const T* __res
   const int b = blockIdx.z;
   const T* src = in + (long long)b * in_bstride;
   const float* s = style ? style + (long long)b * style_stride : nullptr;
-  const unsigned row = OW * cv;
-  for (int oy = blockIdx.y * UPS_ROWS; oy < (int)(blockIdx.y + 1) * UPS_ROWS && oy < 2 * H; ++oy) {
-  int y0, y1;
-  float ly0, ly1;
-  bilinear_src(oy, H, y0, y1, ly0, ly1);
-  const T* r0 = src + (size_t)y0 * W * C;
-  const T* r1 = src + (size_t)y1 * W * C;
-  T* dst = out + ((size_t)b * 2 * H + oy) * OW * C;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < row; i += gridDim.x * blockDim.x) {
-    const unsigned ox = i / cv;
-    const unsigned c = (i - ox * cv) * V;
-    int x0, x1;
-    float lx0, lx1;
-    bilinear_src((int)ox, W, x0, x1, lx0, lx1);
-    float f00[V], f01[V], f10[V], f11[V], o[V];
-    unpack(__ldg(reinterpret_cast<const vec_t*>(r0 + (size_t)x0 * C + c)), f00);
-    unpack(__ldg(reinterpret_cast<const vec_t*>(r0 + (size_t)x1 * C + c)), f01);
-    unpack(__ldg(reinterpret_cast<const vec_t*>(r1 + (size_t)x0 * C + c)), f10);
-    unpack(__ldg(reinterpret_cast<const vec_t*>(r1 + (size_t)x1 * C + c)), f11);
-#pragma unroll
-    for (int j = 0; j < V; ++j) o[j] = ly0 * (lx0 * f00[j] + lx1 * f01[j]) + ly1 * (lx0 * f10[j] + lx1 * f11[j]);
+  T* dstb = out + (size_t)b * 4 * H * W * C;
+  const unsigned rowq = W * cv;
+  const int i_end = min((int)(blockIdx.y + 1) * UPS_ROWS, H);
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < rowq; t += gridDim.x * blockDim.x) {
+    const unsigned j = t / cv;
+    const unsigned c = (t - j * cv) * V;
+    float m[V];
     if (s) {
-      // round to the storage type first: identical to upsample -> cache -> modulate of the AttFind suffix path
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = to_f(from_f<T>(o[j])) * (__ldg(s + c + j) + 1.f);
+      for (int k = 0; k < V; k += 4) {
+        const float4 mv = __ldg(reinterpret_cast<const float4*>(s + c + k));
+        m[k] = mv.x + 1.f; m[k + 1] = mv.y + 1.f; m[k + 2] = mv.z + 1.f; m[k + 3] = mv.w + 1.f;
+      }
     }
-    vec_t v;
-    pack(o, v);
-    *reinterpret_cast<vec_t*>(dst + (size_t)i * V) = v;
-  }
+    const bool jint = j >= 1 && (int)j < W - 1;
+    for (int i = blockIdx.y * UPS_ROWS; i < i_end; ++i) {
+      T* d0 = dstb + ((size_t)(2 * i) * OW + 2 * j) * C + c;   // (2i, 2j); +C: (2i, 2j+1); +OW*C: next row
+      if (jint && i >= 1 && i < H - 1) {
+        float he0[V], ho0[V], he1[V], ho1[V], o[V];
+        {
+          const T* r = src + ((size_t)(i - 1) * W + (j - 1)) * C + c;
+          float a[V], bb[V], cc[V];
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r)), a);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r + C)), bb);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r + 2 * C)), cc);
+#pragma unroll
+          for (int k = 0; k < V; ++k) { he0[k] = 0.25f * a[k] + 0.75f * bb[k]; ho0[k] = 0.75f * bb[k] + 0.25f * cc[k]; }
+        }
+        {
+          const T* r = src + ((size_t)i * W + (j - 1)) * C + c;
+          float a[V], bb[V], cc[V];
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r)), a);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r + C)), bb);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r + 2 * C)), cc);
+#pragma unroll
+          for (int k = 0; k < V; ++k) { he1[k] = 0.25f * a[k] + 0.75f * bb[k]; ho1[k] = 0.75f * bb[k] + 0.25f * cc[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = 0.25f * he0[k] + 0.75f * he1[k];
+        ups_store<T>(d0, o, m, s != nullptr);
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = 0.25f * ho0[k] + 0.75f * ho1[k];
+        ups_store<T>(d0 + C, o, m, s != nullptr);
+        {
+          const T* r = src + ((size_t)(i + 1) * W + (j - 1)) * C + c;
+          float a[V], bb[V], cc[V];
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r)), a);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r + C)), bb);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(r + 2 * C)), cc);
+#pragma unroll
+          for (int k = 0; k < V; ++k) { he0[k] = 0.25f * a[k] + 0.75f * bb[k]; ho0[k] = 0.75f * bb[k] + 0.25f * cc[k]; }   // row i+1
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = 0.75f * he1[k] + 0.25f * he0[k];
+        ups_store<T>(d0 + (size_t)OW * C, o, m, s != nullptr);
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = 0.75f * ho1[k] + 0.25f * ho0[k];
+        ups_store<T>(d0 + (size_t)OW * C + C, o, m, s != nullptr);
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const int oy = 2 * i + (q >> 1), ox = 2 * (int)j + (q & 1);
+          int y0, y1, x0, x1;
+          float ly0, ly1, lx0, lx1;
+          bilinear_src(oy, H, y0, y1, ly0, ly1);
+          bilinear_src(ox, W, x0, x1, lx0, lx1);
+          float f00[V], f01[V], f10[V], f11[V], o[V];
+          unpack(__ldg(reinterpret_cast<const vec_t*>(src + ((size_t)y0 * W + x0) * C + c)), f00);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(src + ((size_t)y0 * W + x1) * C + c)), f01);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(src + ((size_t)y1 * W + x0) * C + c)), f10);
+          unpack(__ldg(reinterpret_cast<const vec_t*>(src + ((size_t)y1 * W + x1) * C + c)), f11);
+#pragma unroll
+          for (int k = 0; k < V; ++k) o[k] = ly0 * (lx0 * f00[k] + lx1 * f01[k]) + ly1 * (lx0 * f10[k] + lx1 * f11[k]);
+          ups_store<T>(dstb + ((size_t)oy * OW + ox) * C + c, o, m, s != nullptr);
+        }
+      }
+    }
   }
 }
 
@@ -120,9 +183,9 @@ int launch_upsample2x_modulate(const T* in, long long in_bstride, const float* s
                                int H, int W, int C, cudaStream_t st) {
   SX_REQUIRE(C % Elem<T>::kVec == 0, "upsample: C=%d not a multiple of %d", C, Elem<T>::kVec);
   if (B == 0) return SX_OK;
-  const int row = 2 * W * (C / Elem<T>::kVec);
+  const int row = W * (C / Elem<T>::kVec);
   const int threads = row >= 256 ? 256 : (row >= 128 ? 128 : 64);
-  dim3 grid((row + threads - 1) / threads, (2 * H + UPS_ROWS - 1) / UPS_ROWS, B);
+  dim3 grid((row + threads - 1) / threads, (H + UPS_ROWS - 1) / UPS_ROWS, B);
   SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "upsample: grid too large");
   upsample2x_modulate_kernel<T><<<grid, threads, 0, st>>>(in, in_bstride, style, style_stride, out, H, W, C);
   SX_CHECK_LAUNCH();
@@ -187,7 +250,7 @@ __global__ void __launch_bounds__(256) torgb_kernel(const T* __restrict__ y2, co
   const int y0 = ty * TH, x0 = tx * TW;
   const int npix = TH * TW;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 3 * Co; i += blockDim.x) {
+  for (int i = tid; y2 != nullptr && i < 3 * Co; i += blockDim.x) {
     const int o = i % Co;
     s_w[i] = (__ldg(rgb_style + (long long)b * style_stride + o) + 1.f) * __ldg(wrgb + i);
   }
@@ -208,7 +271,10 @@ __global__ void __launch_bounds__(256) torgb_kernel(const T* __restrict__ y2, co
   const int ppw = 32 / lpp;                           // pixels per warp iteration
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / lpp, cl = lane - sub * lpp;  // pixel slot in the warp, channel lane
-  for (int p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
+  if (y2 == nullptr) {   // "previous rgb only" mode: rgb = blur(up2x(prev)); the 1x1 conv is fused into the conv2 epilogue
+    for (int pl = tid; pl < npix; pl += blockDim.x) { s_res[pl] = 0.f; s_res[256 + pl] = 0.f; s_res[512 + pl] = 0.f; }
+  }
+  for (int p0 = warp * ppw; y2 != nullptr && p0 < npix; p0 += nwarps * ppw) {
     const int pl = p0 + sub;                          // pixel index in the tile
     const bool live = pl < npix;
     const int py = pl / TW, px = pl - py * TW;
@@ -269,6 +335,21 @@ int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const fl
   dim3 grid((W / TW) * (H / TH), B);
   const size_t smem = (size_t)(3 * Co + 3 * 256 + 3 * (TH + 2) * (TW + 2)) * sizeof(float);
   torgb_kernel<T><<<grid, threads, smem, st>>>(y2, rgb_style, style_stride, wrgb, prev, prev_bstride, rgb, H, W, Co, TH, TW);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+// rgb[b] = blur(upsample2x(prev[b|0]))  -- pre-fills the rgb buffer a fused-ToRGB conv2 epilogue accumulates into
+inline int launch_rgb_prev_up_blur(const float* prev, long long prev_bstride, float* rgb, int B, int H, int W, cudaStream_t st) {
+  if (B == 0) return SX_OK;
+  const int TW = W < 16 ? W : 16, TH = H < 16 ? H : 16;
+  SX_REQUIRE(W % TW == 0 && H % TH == 0, "rgb_prev: H, W must be multiples of the tile");
+  const int npix = TH * TW;
+  const int threads = npix >= 256 ? 256 : (npix >= 64 ? 64 : 32);
+  dim3 grid((W / TW) * (H / TH), B);
+  const int Co = 4;  // dummy: no 1x1 conv in this mode
+  const size_t smem = (size_t)(3 * Co + 3 * 256 + 3 * (TH + 2) * (TW + 2)) * sizeof(float);
+  torgb_kernel<float><<<grid, threads, smem, st>>>(nullptr, nullptr, 0, nullptr, prev, prev_bstride, rgb, H, W, Co, TH, TW);
   SX_CHECK_LAUNCH();
   return SX_OK;
 }

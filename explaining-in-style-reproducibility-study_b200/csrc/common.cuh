@@ -182,6 +182,15 @@ struct ConvEpilogue {
   void* out;                 // NHWC in the activation dtype, or NCHW fp32 (out_nchw_f32)
   int out_nchw_f32;
   void* out_raw;             // optional NHWC copy WITHOUT the next_style factor (clean-prefix cache); null = none
+  // fused ToRGB (RGBBlock ST:618-624) in the epilogue of a block's conv2 (tcgen05 kernels, one N tile, one sample per
+  // M tile):  rgb_out[b,c,y,x] (+)= sum_o act[b,y,x,o] * (rgb_style[b,o] + 1) * rgb_w[c,o]
+  // rgb_out is pre-filled with blur(upsample2x(previous rgb)) when rgb_accumulate != 0.  `out` may then be null
+  // (last block: nothing downstream reads the feature map).
+  const float* rgb_style;    // [B, rgb_style_stride] (pre-offset); null = no fused ToRGB
+  int rgb_style_stride;
+  const float* rgb_w;        // [3][Co]
+  float* rgb_out;            // [B,3,H,W] planar fp32
+  int rgb_accumulate;
 };
 
 }  // namespace sx

@@ -131,7 +131,7 @@ struct TcConfig {
   static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;  // power of two >= 32
   // dynamic smem: [1024 align slack][stages][barriers 256B][tables]
   static size_t smem_bytes(int BB) {
-    return 1024 + (size_t)STAGES * kStageBytes + 256 + (size_t)(2 + 2 * BB) * BLOCK_N * sizeof(float);
+    return 1024 + (size_t)STAGES * kStageBytes + 256 + (size_t)(2 + 2 * BB + 3) * BLOCK_N * sizeof(float);
   }
 };
 
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   float* s_nb = s_nw + BLOCK_N;
   float* s_d = s_nb + BLOCK_N;            // [BB][BLOCK_N] demod coefficients
   float* s_m = s_d + p.BB * BLOCK_N;      // [BB][BLOCK_N] next-layer (style+1)
+  float* s_rgbw = s_m + p.BB * BLOCK_N;   // [3][BLOCK_N] fused-ToRGB weights of the tile's sample (BB == 1 only)
 
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,6 +239,13 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       s_d[i] = (ok && ep.dcoef) ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + o) : 1.f;
       s_m[i] = (ok && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + o) + 1.f : 1.f;
     }
+    const bool fuse_rgb = ep.rgb_style != nullptr;   // host guarantees BB == 1 and a single N tile
+    if (fuse_rgb) {
+      for (int i = et; i < 3 * BLOCK_N; i += 128) {
+        const int o = i % BLOCK_N;
+        s_rgbw[i] = (__ldg(ep.rgb_style + (long long)b0 * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o);
+      }
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
 
     const int q = warp_id & 3;          // TMEM lane quarter this warp may read
@@ -255,6 +263,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
     const float* dd = s_d + bb * BLOCK_N;
     const float* mm = s_m + bb * BLOCK_N;
     const long long pix = ((long long)b * p.H + y) * p.W + x;
+    float rgb_acc[3] = {0.f, 0.f, 0.f};
+    float* rgb_dst = nullptr;
+    if (fuse_rgb && valid) {
+      rgb_dst = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
+      if (ep.rgb_accumulate) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb_acc[c] = __ldg(rgb_dst + (long long)c * p.H * p.W);
+      }
+    }
 
     mbar_wait(tmem_full_bar, 0, 2);
     tc_fence_after();
@@ -275,7 +292,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         fr[j] = t;
         f[j] = t * mm[c0 + j];
       }
-      if (valid) {
+      if (fuse_rgb) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          rgb_acc[0] = fmaf(fr[j], s_rgbw[c0 + j], rgb_acc[0]);
+          rgb_acc[1] = fmaf(fr[j], s_rgbw[BLOCK_N + c0 + j], rgb_acc[1]);
+          rgb_acc[2] = fmaf(fr[j], s_rgbw[2 * BLOCK_N + c0 + j], rgb_acc[2]);
+        }
+      }
+      if (valid && ep.out) {
         if (ep.out_nchw_f32) {
           float* out = reinterpret_cast<float*>(ep.out);
 #pragma unroll
@@ -289,16 +314,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
             *reinterpret_cast<uint4*>(out + j) = pk;
           }
         }
-        if (ep.out_raw) {
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+      }
+      if (valid && ep.out_raw) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            pack(fr + j, pk);
-            *reinterpret_cast<uint4*>(out + j) = pk;
-          }
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          pack(fr + j, pk);
+          *reinterpret_cast<uint4*>(out + j) = pk;
         }
       }
+    }
+    if (rgb_dst) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rgb_dst[(long long)c * p.H * p.W] = rgb_acc[c];
     }
   }
 
@@ -392,6 +421,9 @@ inline int launch_conv_tc(const __nv_bfloat16* x, const __nv_bfloat16* wk, int B
   p.tiles_y = H / p.BH;
   p.ep = ep;
   const int bn = Co % 256 == 0 ? 256 : Co;
+  if (ep.rgb_style && (p.BB != 1 || bn != Co))
+    return fail(SX_EINVAL, "conv_tc: fused ToRGB needs one sample per M tile and a single N tile (H=%d Co=%d)", H, Co);
+  if (!ep.out && !ep.rgb_style) return fail(SX_EINVAL, "conv_tc: no output requested");
   const int bk = Ci % 64 == 0 ? 64 : 32;
 #define SX_TC_CASE(N, K, S) \
   if (bn == N && bk == K) return launch_conv_tc_cfg<N, K, S>(x, wk, p, stream);

@@ -47,18 +47,19 @@ struct HaloCfg {
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
   __host__ __device__ static size_t b_region(int num_b_tiles) { return (size_t)(RESIDENT_B ? num_b_tiles : B_STAGES) * kBBytes; }
   static size_t smem_bytes(int num_b_tiles) {
-    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + 256 + (size_t)(2 + 4) * BLOCK_N * sizeof(float);
+    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + 256 + (size_t)(2 + 4 + 6) * BLOCK_N * sizeof(float);
   }
 };
 
 struct ConvHaloParams {
   int B, H, W, Ci, Co;
   int tiles_x, tiles_y, num_tiles;   // W/8, H/16, B*tiles_y*tiles_x
+  int tx_shift, tpb_shift;           // log2(tiles_x), log2(tiles_x * tiles_y): H, W are powers of two
   int kchunks, num_b_tiles;          // Ci/BLOCK_K, 9*kchunks
   ConvEpilogue ep;
 };
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
 __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                    const __grid_constant__ CUtensorMap tmap_b,
                                                                    const ConvHaloParams p) {
@@ -80,11 +81,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
   float* s_nb = s_nw + BLOCK_N;
   float* s_d = s_nb + BLOCK_N;            // [2][BLOCK_N] demod coefficients of the tile's sample (per accumulator slot)
   float* s_m = s_d + 2 * BLOCK_N;         // [2][BLOCK_N] next-layer (style+1)
+  float* s_rgbw = s_m + 2 * BLOCK_N;      // [2][3][BLOCK_N] fused-ToRGB weights of the tile's sample
 
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BLOCK_N;
-  const int tiles_per_b = p.tiles_x * p.tiles_y;
 
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -114,9 +115,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_b;
-        const int tr = tile - b * tiles_per_b;
-        const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+        const int b = tile >> p.tpb_shift;
+        const int tr = tile - (b << p.tpb_shift);
+        const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
         const int x0 = tx * HALO_BW, y0 = ty * HALO_BH;
         for (int chunk = 0; chunk < p.kchunks; ++chunk) {
           mbar_wait(&a_empty[as], aph ^ 1, 10);
@@ -201,9 +202,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
     // PREFETCHED one tile ahead into registers and published to the other table slot after the current tile is done:
     // their global-load latency used to be exposed once per tile (31 % of all stall samples in ncu).
     auto tile_coords = [&](int tile, int& b, int& x, int& y) {
-      b = tile / tiles_per_b;
-      const int tr = tile - b * tiles_per_b;
-      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      b = tile >> p.tpb_shift;
+      const int tr = tile - (b << p.tpb_shift);
+      const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
       x = tx * HALO_BW + xx;
       y = ty * HALO_BH + yy;
     };
@@ -213,8 +214,27 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
       return __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
     };
     constexpr int TPT = (BLOCK_N + 127) / 128;   // table entries per epilogue thread
-    float d_nx[TPT], m_nx[TPT];
+    constexpr int TPT3 = (3 * BLOCK_N + 127) / 128;
+    constexpr bool fuse_rgb = FUSE_RGB;   // compile-time: the plain instantiation carries none of the ToRGB registers
+    const long long HWl = (long long)p.H * p.W;
+    float d_nx[TPT], m_nx[TPT], w_nx[TPT3];
+    auto load_rgb_prev = [&](int b, int x, int y, float* v) {
+      v[0] = v[1] = v[2] = 0.f;
+      if (fuse_rgb && ep.rgb_accumulate) {
+        const float* src = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __ldg(src + c * HWl);
+      }
+    };
     auto load_tables = [&](int b) {
+      if (fuse_rgb) {
+#pragma unroll
+        for (int k = 0; k < TPT3; ++k) {
+          const int i = et + k * 128;
+          const int o = i % BLOCK_N;
+          w_nx[k] = i < 3 * BLOCK_N ? (__ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o) : 0.f;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < TPT; ++k) {
         const int i = et + k * 128;
@@ -228,12 +248,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
         const int i = et + k * 128;
         if (i < BLOCK_N) { s_d[slot * BLOCK_N + i] = d_nx[k]; s_m[slot * BLOCK_N + i] = m_nx[k]; }
       }
+      if (fuse_rgb) {
+#pragma unroll
+        for (int k = 0; k < TPT3; ++k) {
+          const int i = et + k * 128;
+          if (i < 3 * BLOCK_N) s_rgbw[slot * 3 * BLOCK_N + i] = w_nx[k];
+        }
+      }
     };
     int b = 0, x = 0, y = 0;
-    float nz = 0.f;
+    float nz = 0.f, rgbp[3] = {0.f, 0.f, 0.f};
     if ((int)blockIdx.x < p.num_tiles) {
       tile_coords(blockIdx.x, b, x, y);
       nz = load_noise(b, x, y);
+      load_rgb_prev(b, x, y, rgbp);
       load_tables(b);
       store_tables(0);
     }
@@ -241,14 +269,17 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const float* dd = s_d + acc * BLOCK_N;
       const float* mm = s_m + acc * BLOCK_N;
+      const float* rw = s_rgbw + acc * 3 * BLOCK_N;
+      float rgb_acc[3] = {rgbp[0], rgbp[1], rgbp[2]};
       const long long pix = ((long long)b * p.H + y) * p.W + x;
       // prefetch the next tile's operands (consumed after this tile's TMEM drain)
       const int next = tile + gridDim.x;
       int b2 = 0, x2 = 0, y2 = 0;
-      float nz2 = 0.f;
+      float nz2 = 0.f, rgbp2[3] = {0.f, 0.f, 0.f};
       if (next < p.num_tiles) {
         tile_coords(next, b2, x2, y2);
         nz2 = load_noise(b2, x2, y2);
+        load_rgb_prev(b2, x2, y2, rgbp2);
         load_tables(b2);
       }
       mbar_wait(&tmem_full[acc], accph, 16);
@@ -268,7 +299,16 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
           fr[j] = t;
           f[j] = t * mm[c0 + j];
         }
-        if (ep.out_nchw_f32) {
+        if (fuse_rgb) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            rgb_acc[0] = fmaf(fr[j], rw[c0 + j], rgb_acc[0]);
+            rgb_acc[1] = fmaf(fr[j], rw[BLOCK_N + c0 + j], rgb_acc[1]);
+            rgb_acc[2] = fmaf(fr[j], rw[2 * BLOCK_N + c0 + j], rgb_acc[2]);
+          }
+        }
+        if (!ep.out) {
+        } else if (ep.out_nchw_f32) {
           float* out = reinterpret_cast<float*>(ep.out);
 #pragma unroll
           for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
@@ -293,10 +333,16 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);   // 128 arrivals release the accumulator to the MMA warp
+      if (fuse_rgb) {
+        float* dst = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c * HWl] = rgb_acc[c];
+      }
       acc ^= 1;
       if (acc == 0) accph ^= 1;
       if (next < p.num_tiles) store_tables(acc);
       b = b2; x = x2; y = y2; nz = nz2;
+      rgbp[0] = rgbp2[0]; rgbp[1] = rgbp2[1]; rgbp[2] = rgbp2[2];
       asm volatile("bar.sync 1, 128;" ::: "memory");  // next tile's tables visible; everyone is done with the old slot
     }
   }
@@ -317,8 +363,17 @@ inline bool halo_shape_supported(int Ci, int Co, int H, int W) {
   return true;
 }
 
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
+int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream);
+
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
 int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
+  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true>(x, wk, p, stream);
+  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false>(x, wk, p, stream);
+}
+
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
+int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
   using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -343,7 +398,7 @@ int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHa
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
+  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB>;
   const size_t smem = Cfg::smem_bytes(p.num_b_tiles);
   if (smem > 227 * 1024) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -386,6 +441,10 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
   p.tiles_x = W / HALO_BW; p.tiles_y = H / HALO_BH;
   p.num_tiles = B * p.tiles_x * p.tiles_y;
+  p.tx_shift = 0;
+  while ((1 << p.tx_shift) < p.tiles_x) ++p.tx_shift;
+  p.tpb_shift = 0;
+  while ((1 << p.tpb_shift) < p.tiles_x * p.tiles_y) ++p.tpb_shift;
   p.kchunks = Ci / bk;
   p.num_b_tiles = 9 * p.kchunks;
   p.ep = ep;

@@ -289,17 +289,31 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
       ProfScope ps(32, 0, (double)sizeof(T) * B * HW * co, st);
       SX_TRY(launch_modulate<T>(cache_in(2 * l + 1), 0, styles + g->soff2[l], row, y1m, B, HW, co, st));
     }
-    // ---- conv2: y2 = lrelu(d2 * conv + noise2)
+    // ---- conv2: y2 = lrelu(d2 * conv + noise2)   [+ fused ToRGB on the tcgen05 path]
+    float* rgb_dst = (l == nb - 1) ? rgb_out : ((l & 1) ? rgb_pong : rgb_ping);
+    if (l != nb - 1 && (size_t)B * 3 * HW * 4 > ((l & 1) ? (L.total - L.rgb_b) : (L.rgb_b - L.rgb_a)))
+      return fail(SX_ENOMEM, "internal: rgb scratch too small");
+    // ToRGB is fused into the conv2 epilogue when the kernel has the whole channel row of a pixel in one thread
+    // and one sample per M tile: bf16 path, Co <= 256, H >= 16.
+    static const bool fuse_off = getenv("SX_DISABLE_RGB_FUSION") != nullptr;
+    const bool fuse_rgb = !fuse_off && std::is_same<T, __nv_bfloat16>::value && co <= 256 && H >= 16;
     ep.dcoef = dcoef + g->doff2[l];
     ep.noise_w = g->conv[2 * l + 1].noise_w; ep.noise_b = g->conv[2 * l + 1].noise_b;
     ep.next_style = nullptr; ep.next_style_stride = 0;
     ep.out = y2; ep.out_raw = nullptr;
+    if (fuse_rgb) {
+      if (prev_rgb) {
+        ProfScope ps(34, 0, (double)B * HW * 15, st);
+        SX_TRY(launch_rgb_prev_up_blur(prev_rgb, prev_bstride, rgb_dst, B, H, H, st));
+      }
+      ep.rgb_style = styles + g->soffr[l]; ep.rgb_style_stride = row; ep.rgb_w = g->wrgb[l];
+      ep.rgb_out = rgb_dst; ep.rgb_accumulate = prev_rgb ? 1 : 0;
+      if (l == nb - 1) ep.out = nullptr;   // nothing reads the last feature map
+    }
     SX_TRY(run_conv<T>(g, 2 * l + 1, y1m, B, co, co, H, ep, st));
-    // ---- ToRGB (+ upsample/blur of the previous rgb)
-    float* rgb_dst = (l == nb - 1) ? rgb_out : ((l & 1) ? rgb_pong : rgb_ping);
-    if (l != nb - 1 && (size_t)B * 3 * HW * 4 > ((l & 1) ? (L.total - L.rgb_b) : (L.rgb_b - L.rgb_a)))
-      return fail(SX_ENOMEM, "internal: rgb scratch too small");
-    {
+    ep.rgb_style = nullptr; ep.rgb_out = nullptr;
+    // ---- ToRGB (+ upsample/blur of the previous rgb), standalone where it is not fused
+    if (!fuse_rgb) {
       ProfScope ps(34, 2.0 * 3 * co * (double)HW * B, (double)B * HW * (sizeof(T) * co + 12 + (prev_rgb ? 3 : 0)), st);
       SX_TRY(launch_torgb<T>(y2, styles + g->soffr[l], row, g->wrgb[l], prev_rgb, prev_bstride, rgb_dst, B, H, H, co, st));
     }
