@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--classifier-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--classifier-mode", default="fused", choices=["fused", "eager"],
                     help="fused: BatchNorm folded + PyTorch's fused cuDNN conv+bias+ReLU ops; eager: the module as is")
+    ap.add_argument("--preprocess", default="native", choices=["native", "torch"],
+                    help="classifier input pipeline: one native kernel or torchvision resize + Normalize")
     ap.add_argument("--latents-per-step", type=int, default=1)
     ap.add_argument("--pool", type=int, default=16, help="latents per rank prepared up front (minima/maxima pool)")
     ap.add_argument("--max-batch", type=int, default=128)
@@ -187,7 +189,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = evals / dt
     sample = f"per step: 1 latent x {n_coords} style coords (every {O.num_style_coords(sd) // n_coords}th) x 2 directions + base image, batch 1"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -195,7 +197,7 @@ def run_reference(args):
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -253,6 +255,22 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001 -- any failure means: keep the eager module, say so in the JSON
             clf.fused = None
             clf_mode = f"eager (fused path unavailable: {type(e).__name__}: {str(e)[:120]})"
+
+    pre_mode = "torch (resize, sub, div, cast, permute)"
+    if args.preprocess == "native" and kind == "resnet":
+        try:
+            probe = calib[:8]
+            ref_logits = clf.classify_images(probe)
+            clf.use_native_preprocess(True)
+            got = clf.classify_images(probe)
+            torch.cuda.synchronize()
+            tol = 0.03 * float(ref_logits.abs().max()) + 0.03
+            if not torch.isfinite(got).all() or float((got - ref_logits).abs().max()) > tol:
+                raise RuntimeError(f"native preprocess deviates: {float((got - ref_logits).abs().max()):.3e} > {tol:.3e}")
+            pre_mode = "native (sx_resize_aa_normalize: antialiased resize + normalise + cast + NHWC in one kernel)"
+        except Exception as e:  # noqa: BLE001
+            clf.native_preprocess = False
+            pre_mode = f"torch (native preprocess unavailable: {type(e).__name__}: {str(e)[:120]})"
 
     class TimedClassifier:
         """records CUDA events around every classifier call so the step breakdown can name the PyTorch share."""
@@ -365,6 +383,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---------------- roofline of the dominant kernel (Conv2DMod tcgen05 / FFMA) ----------------
@@ -421,19 +440,36 @@ def run_ours(args):
         "config": {"workload": f"StylEx {size}px FFHQ-shaped generator (capacity 16, S={S}) + {kind}-18@224 classifier; "
                                f"AttFind sweep, {lps} latent(s)/rank/step x {S} coords x 2 directions",
                    "coord_evals_per_step": int(2 * S * lps * world), "max_batch": args.max_batch,
-                   "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)", "classifier_mode": clf_mode,
+                   "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)", "classifier_mode": clf_mode, "classifier_preprocess": pre_mode,
                    "prefix_reuse": True, "l2": "inputs larger than L2: every 128-eval batch streams >2 GB of activations (L2 = 126 MB)",
                    "pool_latents": pool_n, "parallelism": f"latent-sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roofline, "cpu_baseline": cpu,
         "conv_flops_per_full_image": conv_flops_per_image(plan.pairs),
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Everything third parties print to stdout (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is written
+    to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, line)
 
 
 if __name__ == "__main__":
     a = parse()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

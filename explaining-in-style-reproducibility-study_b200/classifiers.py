@@ -72,7 +72,42 @@ class _Wrapper:
         self.fused = FusedResNetInference(self.model, self.compute_dtype)
         return self
 
+    native_preprocess = False
+
+    def use_native_preprocess(self, on: bool = True):
+        """Opt-in: run resize(antialias bilinear) + Normalize + cast + channels_last as ONE native kernel
+        (sx_resize_aa_normalize) instead of five PyTorch passes.  Same arithmetic as ATen's antialiased bilinear
+        kernel; the network forward stays PyTorch.  Only the ResNet wrapper (224x224 resize) has this path."""
+        if on and self.kind != "resnet":
+            raise NotImplementedError("native preprocessing covers the ResNet wrapper (resize to 224) only")
+        self.native_preprocess = on
+        return self
+
+    def _native_pre(self, images: torch.Tensor) -> torch.Tensor:
+        import ctypes
+        from . import _native as N
+
+        N.require_cuda(images)
+        N.device_check()
+        x = N.f32c(images)
+        b, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("native preprocessing expects 3-channel images")
+        d = self.resnet_dim
+        out = torch.empty((b, 3, d, d), device=x.device, dtype=self.compute_dtype, memory_format=torch.channels_last)
+        if self.compute_dtype not in (torch.float32, torch.bfloat16):
+            raise NotImplementedError("native preprocessing writes fp32 or bf16")
+        mean = (ctypes.c_float * 3)(*_MEAN)
+        std = (ctypes.c_float * 3)(*_STD)
+        N.check(N.lib().sx_resize_aa_normalize(x.data_ptr(), out.data_ptr(), 1 if self.compute_dtype == torch.bfloat16 else 0, b,
+                                               h, w, d, d, 1 if self.normalize else 0, mean, std, N.stream_ptr()),
+                "sx_resize_aa_normalize")
+        return out
+
     def classify_images(self, images) -> torch.Tensor:
+        if self.native_preprocess and isinstance(images, torch.Tensor):
+            x = self._native_pre(images)
+            return (self.fused(x) if self.fused is not None else self.model(x)).float()
         x = self.preprocess(images)
         if self.compute_dtype != torch.float32 or self.channels_last:
             x = x.to(dtype=self.compute_dtype, memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)

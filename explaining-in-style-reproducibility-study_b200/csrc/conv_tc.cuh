@@ -116,6 +116,50 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
+// ---- epilogue math on 32 accumulator columns of one output pixel (shared by both tcgen05 kernels) ----------------
+// All per-column operands come from shared-memory tables read as float4 (7 LDS.128 per 4 columns instead of 28 LDS.32:
+// the epilogue of the narrow layers is issue-bound, and these loads were most of its instructions).
+__device__ __forceinline__ void epi_chunk32(const uint32_t* __restrict__ v, const float* __restrict__ dd, const float* __restrict__ nw,
+                                            const float* __restrict__ nb, const float* __restrict__ mm, float nz, int act,
+                                            bool round_bf16, float* __restrict__ f, float* __restrict__ fr) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dd + j);
+    const float4 w4 = *reinterpret_cast<const float4*>(nw + j);
+    const float4 b4 = *reinterpret_cast<const float4*>(nb + j);
+    const float4 m4 = *reinterpret_cast<const float4*>(mm + j);
+    const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float t = __uint_as_float(v[j + k]) * dv[k];
+      t += nz * wv[k] + bv[k];
+      if (act) t = lrelu02(t);
+      // round the raw activation to the storage type BEFORE the next layer's modulation: the AttFind suffix path
+      // re-modulates the cached (bf16) raw tensor, and both paths must produce bit-identical conv inputs
+      if (round_bf16) t = __bfloat162float(__float2bfloat16_rn(t));
+      fr[j + k] = t;
+      f[j + k] = t * mv[k];
+    }
+  }
+}
+// fused ToRGB partial sums over the same 32 columns: acc[c] += sum_j fr[j] * rw[c * stride + j]
+__device__ __forceinline__ void rgb_chunk32(const float* __restrict__ fr, const float* __restrict__ rw, int stride, float* __restrict__ acc) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float a = acc[c];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(rw + c * stride + j);
+      a = fmaf(fr[j], w4.x, a);
+      a = fmaf(fr[j + 1], w4.y, a);
+      a = fmaf(fr[j + 2], w4.z, a);
+      a = fmaf(fr[j + 3], w4.w, a);
+    }
+    acc[c] = a;
+  }
+}
+
 struct ConvTcParams {
   int B, H, W, Ci, Co, KS;
   int BW, BH, BB;            // pixel box of one M tile: BB*BH*BW == 128
@@ -281,25 +325,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
       float f[32], fr[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]) * dd[c0 + j];
-        t += nz * s_nw[c0 + j] + s_nb[c0 + j];
-        if (ep.act) t = lrelu02(t);
-        // round the raw activation to the storage type BEFORE the next layer's modulation: the AttFind suffix path
-        // re-modulates the cached (bf16) raw tensor, and both paths must produce bit-identical conv inputs
-        if (!ep.out_nchw_f32) t = __bfloat162float(__float2bfloat16_rn(t));
-        fr[j] = t;
-        f[j] = t * mm[c0 + j];
-      }
-      if (fuse_rgb) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          rgb_acc[0] = fmaf(fr[j], s_rgbw[c0 + j], rgb_acc[0]);
-          rgb_acc[1] = fmaf(fr[j], s_rgbw[BLOCK_N + c0 + j], rgb_acc[1]);
-          rgb_acc[2] = fmaf(fr[j], s_rgbw[2 * BLOCK_N + c0 + j], rgb_acc[2]);
-        }
-      }
+      epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
+      if (fuse_rgb) rgb_chunk32(fr, s_rgbw + c0, BLOCK_N, rgb_acc);
       if (valid && ep.out) {
         if (ep.out_nchw_f32) {
           float* out = reinterpret_cast<float*>(ep.out);

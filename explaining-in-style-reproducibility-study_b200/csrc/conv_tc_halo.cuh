@@ -290,23 +290,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
         tmem_ld_wait();
         float f[32], fr[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(v[j]) * dd[c0 + j];
-          t += nz * s_nw[c0 + j] + s_nb[c0 + j];
-          if (ep.act) t = lrelu02(t);
-          if (!ep.out_nchw_f32) t = __bfloat162float(__float2bfloat16_rn(t));  // see conv_tc.cuh: round before modulating
-          fr[j] = t;
-          f[j] = t * mm[c0 + j];
-        }
-        if (fuse_rgb) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            rgb_acc[0] = fmaf(fr[j], rw[c0 + j], rgb_acc[0]);
-            rgb_acc[1] = fmaf(fr[j], rw[BLOCK_N + c0 + j], rgb_acc[1]);
-            rgb_acc[2] = fmaf(fr[j], rw[2 * BLOCK_N + c0 + j], rgb_acc[2]);
-          }
-        }
+        epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
+        if (fuse_rgb) rgb_chunk32(fr, rw + c0, BLOCK_N, rgb_acc);
         if (!ep.out) {
         } else if (ep.out_nchw_f32) {
           float* out = reinterpret_cast<float*>(ep.out);

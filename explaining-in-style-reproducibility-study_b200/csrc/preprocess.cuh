@@ -1,0 +1,100 @@
+// preprocess.cuh -- the tensor branch of the classifier wrappers' preprocessing as ONE kernel:
+//   torchvision.transforms.functional.resize(images, [OH, OW])   (bilinear, antialias=True: torch's
+//   _upsample_bilinear2d_aa)  ->  Normalize(mean, std)  ->  cast  ->  channels_last
+// (reference resnet_classifier.py:60-68).  In PyTorch this is five passes over the batch (antialiased resize, sub, div,
+// dtype cast, layout change: ~0.65 ms per 128 images at 256px, 9 % of the AttFind step); here it is one read of the
+// image and one write of the network input.  The network itself stays PyTorch.
+//
+// Arithmetic follows ATen's CUDA kernel (aten/src/ATen/native/cuda/UpSampleBilinear2d.cu, upsample_gen2d_aa_out_frame):
+//   scale = in / out;  support = scale >= 1 ? scale : 1;  invscale = scale >= 1 ? 1 / scale : 1
+//   center = scale * (i + 0.5);  xmin = max(int(center - support + 0.5), 0);  xsize = min(int(center + support + 0.5), in) - xmin
+//   w_j = tri((j + xmin - center + 0.5) * invscale), normalised by their sum;   tri(x) = max(0, 1 - |x|)
+//   out = sum_y wy[y] * (sum_x wx[x] * src[ymin + y][xmin + x])               (fp32 accumulation in this order)
+#pragma once
+
+#include "common.cuh"
+
+namespace sx {
+
+constexpr int AA_MAX_TAPS = 12;  // support <= 5.5 input pixels per side (scale <= 5.5)
+
+template <int TAPS>
+__device__ __forceinline__ void aa_weights(int i, float scale, float support, float invscale, int in_size, int& xmin, int& xsize,
+                                           float* w) {
+  const float center = scale * (i + 0.5f);
+  xmin = max((int)(center - support + 0.5f), 0);
+  xsize = min((int)(center + support + 0.5f), in_size) - xmin;
+  xsize = xsize < TAPS ? xsize : TAPS;
+  float total = 0.f;
+#pragma unroll
+  for (int j = 0; j < TAPS; ++j) {
+    float x = (j + xmin - center + 0.5f) * invscale;
+    x = fabsf(x);
+    const float v = (j < xsize && x < 1.f) ? 1.f - x : 0.f;
+    w[j] = v;
+    total += v;
+  }
+  if (total != 0.f) {
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) w[j] /= total;
+  }
+}
+
+struct Norm3 {
+  float mean[3], std[3];
+  int on;
+};
+
+// in [B,3,IH,IW] fp32 NCHW  ->  out [B,OH,OW,3] (T) = a channels_last [B,3,OH,OW] tensor
+template <typename T, int TAPS>
+__global__ void __launch_bounds__(256) resize_aa_normalize_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int IH, int IW,
+                                                                  int OH, int OW, Norm3 nm) {
+  const float sy = (float)IH / (float)OH, sx_ = (float)IW / (float)OW;
+  const float sup_y = sy >= 1.f ? sy : 1.f, sup_x = sx_ >= 1.f ? sx_ : 1.f;
+  const float inv_y = sy >= 1.f ? 1.f / sy : 1.f, inv_x = sx_ >= 1.f ? 1.f / sx_ : 1.f;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  if (ox >= OW) return;
+  float wx[TAPS], wy[TAPS];
+  int xmin, xsize, ymin, ysize;
+  aa_weights<TAPS>(ox, sx_, sup_x, inv_x, IW, xmin, xsize, wx);
+  aa_weights<TAPS>(oy, sy, sup_y, inv_y, IH, ymin, ysize, wy);
+  T* dst = out + (((size_t)b * OH + oy) * OW + ox) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* plane = in + ((size_t)b * 3 + c) * IH * IW;
+    float acc = 0.f;
+#pragma unroll
+    for (int y = 0; y < TAPS; ++y) {
+      if (y < ysize) {
+        const float* row = plane + (size_t)(ymin + y) * IW + xmin;
+        float t = __ldg(row) * wx[0];
+#pragma unroll
+        for (int x = 1; x < TAPS; ++x)
+          if (x < xsize) t += __ldg(row + x) * wx[x];
+        acc = y == 0 ? t * wy[0] : acc + t * wy[y];
+      }
+    }
+    if (nm.on) acc = (acc - nm.mean[c]) / nm.std[c];
+    dst[c] = from_f<T>(acc);
+  }
+}
+
+template <typename T>
+int launch_resize_aa_normalize(const float* in, T* out, int B, int IH, int IW, int OH, int OW, const Norm3& nm, cudaStream_t st) {
+  if (B == 0) return SX_OK;
+  const float sy = (float)IH / OH, sxx = (float)IW / OW;
+  const float sup = fmaxf(sy >= 1.f ? sy : 1.f, sxx >= 1.f ? sxx : 1.f);
+  const int taps = (int)(2.f * sup) + 2;
+  SX_REQUIRE(taps <= AA_MAX_TAPS, "resize: scale factor %.2f too large (max %d taps)", sup, AA_MAX_TAPS);
+  dim3 grid((OW + 255) / 256, OH, B);
+  SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "resize: grid too large");
+  if (taps <= 4)
+    resize_aa_normalize_kernel<T, 4><<<grid, 256, 0, st>>>(in, out, B, IH, IW, OH, OW, nm);
+  else
+    resize_aa_normalize_kernel<T, AA_MAX_TAPS><<<grid, 256, 0, st>>>(in, out, B, IH, IW, OH, OW, nm);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+}  // namespace sx

@@ -89,6 +89,13 @@ int sx_rgb_add_upsample_blur(const float* rgb, const float* prev, float* out, in
 int sx_linear_fwd(const float* x, const float* weight, const float* bias, float* out, int B, int in_features,
                   int out_features, sx_stream_t stream);
 
+/* The tensor branch of ResNet.classify_images' preprocessing (resnet_classifier.py:60-68) in one pass:
+ * torchvision resize(images, [OH,OW]) (bilinear, antialias=True: ATen's _upsample_bilinear2d_aa arithmetic) ->
+ * Normalize(mean, std) (optional) -> cast -> channels_last.  in [B,3,IH,IW] fp32 NCHW; out [B,OH,OW,3] fp32 or bf16,
+ * i.e. the memory of a channels_last [B,3,OH,OW] tensor.  mean3/std3: HOST arrays of 3 floats.  The network stays PyTorch. */
+int sx_resize_aa_normalize(const float* in, void* out, int out_bf16, int B, int IH, int IW, int OH, int OW, int normalize,
+                           const float* mean3, const float* std3, sx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Generator plan -- sits under Generator.forward (ST:794-825) and the notebook's repeated
  * stylex.G(w, noise) calls (NB:318,382).

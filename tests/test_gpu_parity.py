@@ -418,6 +418,32 @@ def test_fused_classifier_matches_eager(dev, dtype, tol):
     assert float((got - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("size", [256, 64, 224, 300])
+def test_native_preprocess_matches_torchvision(dev, size):
+    """sx_resize_aa_normalize == torchvision resize(antialias bilinear) + Normalize (+ cast, channels_last)."""
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 224 * 224, 2)).to(dev)
+    clf = sx.make_classifier("resnet", model, size)
+    g = torch.Generator().manual_seed(size)
+    imgs = (torch.rand(5, 3, size, size, generator=g) * 4 - 1.5).to(dev)
+    ref = clf.preprocess(imgs)
+    got = clf._native_pre(imgs)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    err = float((got - ref).abs().max())
+    assert err <= 2e-5 * max(1.0, float(ref.abs().max())), err
+    clf.set_compute(torch.bfloat16, channels_last=True)
+    got16 = clf._native_pre(imgs)
+    assert got16.dtype == torch.bfloat16
+    assert float((got16.float() - ref.to(torch.bfloat16).float()).abs().max()) <= 0.07   # <= 1 bf16 ulp at |x| < 16
+    clf.set_compute(torch.float32)
+    clf.use_native_preprocess(True)
+    a = clf.classify_images(imgs)
+    clf.use_native_preprocess(False)
+    b = clf.classify_images(imgs)
+    assert float((a - b).abs().max()) <= 1e-3 * max(1.0, float(b.abs().max()))
+    with pytest.raises(NotImplementedError):
+        sx.make_classifier("mobilenet", model, size).use_native_preprocess(True)
+
+
 def test_native_launches_counted(dev):
     before = _native.launch_count()
     sx.modules.upsample2x(torch.zeros(1, 1, 4, 4, device=dev))
