@@ -401,7 +401,7 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    bw = {k: v for k, v in prof.items() if k in (32, 33, 34)}
+    bw = {k: v for k, v in prof.items() if k in (32, 33, 34, 37)}
     bw_ms = sum(v["ms"] for v in bw.values())
     bw_bytes = sum(v["bytes"] for v in bw.values())
     all_ms = sum(v["ms"] for v in prof.values())
@@ -418,7 +418,7 @@ def run_ours(args):
                         "share_of_step": bw_ms / ms if ms else None},
         "native_kernels_share_of_step": all_ms / ms if ms else None,
         "classifier_share_of_step": clf_ms / ms if ms else None,
-        "kernel_ms_per_step": {{32: "modulate", 33: "upsample2x_modulate", 34: "torgb", 35: "demod"}.get(k, f"conv{k}"):
+        "kernel_ms_per_step": {{32: "modulate", 33: "upsample2x_modulate", 34: "torgb", 35: "demod", 37: "rgb_prev_up_blur"}.get(k, f"conv{k}"):
                                round(v["ms"] / max(1, args.steps), 3) for k, v in sorted(prof.items())},
     }
 

@@ -58,8 +58,9 @@ size_t sx_conv2dmod_workspace_bytes(int B, int Ci, int Co, int H, int W, int k, 
 
 int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, float* out, int B, int Ci, int Co, int H, int W,
                      int k, int demod, float eps, int precision, void* workspace, size_t ws_bytes, sx_stream_t stream) {
-  SX_REQUIRE(x && weight && style && out && workspace, "null argument");
   SX_REQUIRE(B >= 0 && Ci >= 1 && Co >= 1 && H >= 1 && W >= 1, "bad shape B=%d Ci=%d Co=%d H=%d W=%d", B, Ci, Co, H, W);
+  if (B == 0) return SX_OK;
+  SX_REQUIRE(x && weight && style && out && workspace, "null argument");
   SX_REQUIRE(k == 1 || k == 3, "kernel size %d not supported (1 or 3)", k);
   SX_REQUIRE(precision == SX_PREC_FP32 || precision == SX_PREC_BF16, "precision=%d", precision);
   SX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
@@ -121,10 +122,10 @@ int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, fl
 }
 
 int sx_upsample2x_bilinear(const float* x, float* out, int B, int C, int H, int W, sx_stream_t stream) {
-  SX_REQUIRE(x && out, "null argument");
   SX_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1, "bad shape");
   const long long planes = (long long)B * C;
   if (planes == 0) return SX_OK;
+  SX_REQUIRE(x && out, "null argument");
   upsample2x_nchw_kernel<<<ew_grid(planes * 4 * H * W, 256), 256, 0, S(stream)>>>(x, out, planes, H, W);
   SX_CHECK_LAUNCH();
   return SX_OK;

@@ -331,7 +331,7 @@ int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const fl
   const int TW = W < 16 ? W : 16, TH = H < 16 ? H : 16;
   SX_REQUIRE(W % TW == 0 && H % TH == 0, "torgb: H, W must be multiples of the tile");
   const int npix = TH * TW;
-  const int threads = npix >= 256 ? 256 : (npix >= 64 ? 64 : 32);
+  const int threads = npix >= 256 ? 256 : 128;   // >= 128: the 3*Co-entry weight table fill is a chain of dependent loads
   dim3 grid((W / TW) * (H / TH), B);
   const size_t smem = (size_t)(3 * Co + 3 * 256 + 3 * (TH + 2) * (TW + 2)) * sizeof(float);
   torgb_kernel<T><<<grid, threads, smem, st>>>(y2, rgb_style, style_stride, wrgb, prev, prev_bstride, rgb, H, W, Co, TH, TW);
@@ -339,17 +339,47 @@ int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const fl
   return SX_OK;
 }
 
-// rgb[b] = blur(upsample2x(prev[b|0]))  -- pre-fills the rgb buffer a fused-ToRGB conv2 epilogue accumulates into
+// rgb[b] = blur(upsample2x(prev[b|0]))  -- pre-fills the rgb buffer a fused-ToRGB conv2 epilogue accumulates into.
+// Interior pixels use the closed form of blur([1,2,1]/4) o bilinear-upsample: per axis a 3-tap filter on the low-res
+// neighbourhood {i-1, i, i+1} with weights (5,10,1)/16 for even and (1,10,5)/16 for odd output coordinates
+// (9 loads + 9 FMAs per channel); pixels whose neighbourhood touches the border (index clamping of the upsample,
+// reflect padding of the blur) take the generic two-step evaluation.
+__global__ void __launch_bounds__(256) rgb_prev_up_blur_kernel(const float* __restrict__ prev, long long prev_bstride,
+                                                               float* __restrict__ rgb, int h, int w) {
+  const int H = 2 * h, W = 2 * w;
+  const int b = blockIdx.z;
+  const int y = blockIdx.y;
+  const float* pp = prev + (long long)b * prev_bstride;
+  float* dst = rgb + (long long)b * 3 * H * W;
+  const int i = y >> 1;
+  const bool yint = i >= 1 && i <= h - 2;
+  const float wy0 = (y & 1) ? 0.0625f : 0.3125f, wy2 = (y & 1) ? 0.3125f : 0.0625f;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    const int j = x >> 1;
+    if (yint && j >= 1 && j <= w - 2) {
+      const float wx0 = (x & 1) ? 0.0625f : 0.3125f, wx2 = (x & 1) ? 0.3125f : 0.0625f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* p = pp + (size_t)c * h * w + (size_t)(i - 1) * w + (j - 1);
+        const float r0 = wx0 * __ldg(p) + 0.625f * __ldg(p + 1) + wx2 * __ldg(p + 2);
+        const float r1 = wx0 * __ldg(p + w) + 0.625f * __ldg(p + w + 1) + wx2 * __ldg(p + w + 2);
+        const float r2 = wx0 * __ldg(p + 2 * w) + 0.625f * __ldg(p + 2 * w + 1) + wx2 * __ldg(p + 2 * w + 2);
+        dst[((size_t)c * H + y) * W + x] = wy0 * r0 + 0.625f * r1 + wy2 * r2;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dst[((size_t)c * H + y) * W + x] = up2_blur(pp + (size_t)c * h * w, nullptr, h, w, y, x);
+    }
+  }
+}
+
 inline int launch_rgb_prev_up_blur(const float* prev, long long prev_bstride, float* rgb, int B, int H, int W, cudaStream_t st) {
   if (B == 0) return SX_OK;
-  const int TW = W < 16 ? W : 16, TH = H < 16 ? H : 16;
-  SX_REQUIRE(W % TW == 0 && H % TH == 0, "rgb_prev: H, W must be multiples of the tile");
-  const int npix = TH * TW;
-  const int threads = npix >= 256 ? 256 : (npix >= 64 ? 64 : 32);
-  dim3 grid((W / TW) * (H / TH), B);
-  const int Co = 4;  // dummy: no 1x1 conv in this mode
-  const size_t smem = (size_t)(3 * Co + 3 * 256 + 3 * (TH + 2) * (TW + 2)) * sizeof(float);
-  torgb_kernel<float><<<grid, threads, smem, st>>>(nullptr, nullptr, 0, nullptr, prev, prev_bstride, rgb, H, W, Co, TH, TW);
+  SX_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 4 && W >= 4, "rgb_prev: bad size %dx%d", H, W);
+  const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : (W >= 64 ? 64 : 32));
+  dim3 grid((W + threads - 1) / threads, H, B);
+  SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "rgb_prev: grid too large");
+  rgb_prev_up_blur_kernel<<<grid, threads, 0, st>>>(prev, prev_bstride, rgb, H / 2, W / 2);
   SX_CHECK_LAUNCH();
   return SX_OK;
 }

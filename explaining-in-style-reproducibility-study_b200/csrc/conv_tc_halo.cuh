@@ -55,12 +55,19 @@ struct ConvHaloParams {
   int B, H, W, Ci, Co;
   int tiles_x, tiles_y, num_tiles;   // W/8, H/16, B*tiles_y*tiles_x
   int tx_shift, tpb_shift;           // log2(tiles_x), log2(tiles_x * tiles_y): H, W are powers of two
+  int debug;                         // SX_HALO_DEBUG bitmask (bottleneck experiments; results are garbage when set):
+                                     //   1 skip epilogue math/stores, 2 skip MMA issue, 4 skip activation TMA loads
   int kchunks, num_b_tiles;          // Ci/BLOCK_K, 9*kchunks
   ConvEpilogue ep;
 };
 
+// resident CTAs per SM the register budget is compiled for: the narrow layers' per-tile chain (TMEM wait -> ld ->
+// math -> barrier) is latency-bound, so more independent CTAs per SM is what hides it
+template <int BLOCK_N, int BLOCK_K>
+constexpr int halo_min_ctas() { return BLOCK_N == 32 ? 2 : 1; }   // 2 CTAs/SM where smem allows it; 3 (96 regs, spills) measured slower
+
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
-__global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a,
+__global__ void __launch_bounds__(NUM_THREADS, halo_min_ctas<BLOCK_N, BLOCK_K>()) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                    const __grid_constant__ CUtensorMap tmap_b,
                                                                    const ConvHaloParams p) {
   using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
@@ -86,6 +93,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BLOCK_N;
+#ifdef SX_HALO_DEBUG_KNOBS   // bottleneck experiments only (profiles/README.md); never in the shipped library
+  const int dbg = p.debug;
+#else
+  constexpr int dbg = 0;
+#endif
 
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -121,8 +133,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
         const int x0 = tx * HALO_BW, y0 = ty * HALO_BH;
         for (int chunk = 0; chunk < p.kchunks; ++chunk) {
           mbar_wait(&a_empty[as], aph ^ 1, 10);
-          mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
-          tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+          if (dbg & 4) {
+            mbar_arrive(&a_full[as]);
+          } else {
+            mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
+            tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+          }
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
           if (!RESIDENT_B) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -168,9 +184,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint64_t da = make_smem_desc_sbo<BLOCK_K>(a_base + (uint32_t)((ky * HALO_W + kx) * Cfg::kRowBytes), sbo);
             const uint64_t db = make_smem_desc<BLOCK_K>(b_addr);
+            if (!(dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+            }
             if (!RESIDENT_B) {
               umma_commit(&b_empty[bs]);
               if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
@@ -217,7 +235,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
     constexpr int TPT3 = (3 * BLOCK_N + 127) / 128;
     constexpr bool fuse_rgb = FUSE_RGB;   // compile-time: the plain instantiation carries none of the ToRGB registers
     const long long HWl = (long long)p.H * p.W;
-    float d_nx[TPT], m_nx[TPT], w_nx[TPT3];
+    // raw prefetched values only: NO arithmetic on them before the tile has been processed, otherwise the load latency
+    // lands on the per-tile critical path again (ncu: long_scoreboard on the `+ 1` of the style rows)
+    float d_nx[TPT], m_nx[TPT], ws_nx[TPT3], ww_nx[TPT3];
     auto load_rgb_prev = [&](int b, int x, int y, float* v) {
       v[0] = v[1] = v[2] = 0.f;
       if (fuse_rgb && ep.rgb_accumulate) {
@@ -232,27 +252,29 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
         for (int k = 0; k < TPT3; ++k) {
           const int i = et + k * 128;
           const int o = i % BLOCK_N;
-          w_nx[k] = i < 3 * BLOCK_N ? (__ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o) : 0.f;
+          const bool in = i < 3 * BLOCK_N;
+          ws_nx[k] = in ? __ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) : 0.f;
+          ww_nx[k] = in ? __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o) : 0.f;
         }
       }
 #pragma unroll
       for (int k = 0; k < TPT; ++k) {
         const int i = et + k * 128;
         d_nx[k] = (i < BLOCK_N && ep.dcoef) ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + i) : 1.f;
-        m_nx[k] = (i < BLOCK_N && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) + 1.f : 1.f;
+        m_nx[k] = (i < BLOCK_N && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) : 0.f;
       }
     };
     auto store_tables = [&](int slot) {
 #pragma unroll
       for (int k = 0; k < TPT; ++k) {
         const int i = et + k * 128;
-        if (i < BLOCK_N) { s_d[slot * BLOCK_N + i] = d_nx[k]; s_m[slot * BLOCK_N + i] = m_nx[k]; }
+        if (i < BLOCK_N) { s_d[slot * BLOCK_N + i] = d_nx[k]; s_m[slot * BLOCK_N + i] = m_nx[k] + 1.f; }
       }
       if (fuse_rgb) {
 #pragma unroll
         for (int k = 0; k < TPT3; ++k) {
           const int i = et + k * 128;
-          if (i < 3 * BLOCK_N) s_rgbw[slot * 3 * BLOCK_N + i] = w_nx[k];
+          if (i < 3 * BLOCK_N) s_rgbw[slot * 3 * BLOCK_N + i] = (ws_nx[k] + 1.f) * ww_nx[k];
         }
       }
     };
@@ -285,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_halo_kernel(const __grid_
       mbar_wait(&tmem_full[acc], accph, 16);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < ((dbg & 1) ? 0 : BLOCK_N); c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
         tmem_ld_wait();
@@ -430,6 +452,8 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   while ((1 << p.tx_shift) < p.tiles_x) ++p.tx_shift;
   p.tpb_shift = 0;
   while ((1 << p.tpb_shift) < p.tiles_x * p.tiles_y) ++p.tpb_shift;
+  static const int dbg = getenv("SX_HALO_DEBUG") ? atoi(getenv("SX_HALO_DEBUG")) : 0;
+  p.debug = dbg;
   p.kchunks = Ci / bk;
   p.num_b_tiles = 9 * p.kchunks;
   p.ep = ep;

@@ -144,8 +144,9 @@ inline int generator_load(sx_generator* g, const float* initial_block, const flo
 
 inline int generator_styles(const sx_generator* g, const float* w, float* styles, int B, cudaStream_t st) {
   SX_REQUIRE(g && g->loaded, "generator not loaded");
-  SX_REQUIRE(w && styles && B >= 0, "bad argument");
+  SX_REQUIRE(B >= 0, "B=%d", B);
   if (B == 0) return SX_OK;
+  SX_REQUIRE(w && styles, "null argument");
   const long long warps = (long long)B * g->style_row;
   styles_affine_kernel<<<ew_grid(warps * 32, 256, 16), 256, 0, st>>>(w, g->affine_w, g->affine_b, g->col_layer, styles, B,
                                                                   g->num_blocks, g->latent, g->style_row);
@@ -303,7 +304,7 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
     ep.out = y2; ep.out_raw = nullptr;
     if (fuse_rgb) {
       if (prev_rgb) {
-        ProfScope ps(34, 0, (double)B * HW * 15, st);
+        ProfScope ps(37, 0, (double)B * HW * 15, st);
         SX_TRY(launch_rgb_prev_up_blur(prev_rgb, prev_bstride, rgb_dst, B, H, H, st));
       }
       ep.rgb_style = styles + g->soffr[l]; ep.rgb_style_stride = row; ep.rgb_w = g->wrgb[l];
@@ -328,8 +329,9 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
 inline int generator_forward(sx_generator* g, const float* styles, const float* inoise, int noise_batch, float* rgb_out, int B,
                              int start_conv, int save_cache, int precision, void* workspace, size_t ws_bytes, cudaStream_t st) {
   SX_REQUIRE(g && g->loaded, "generator not loaded");
-  SX_REQUIRE(styles && inoise && rgb_out && workspace, "null argument");
   SX_REQUIRE(B >= 0, "B=%d", B);
+  if (B == 0) return SX_OK;
+  SX_REQUIRE(styles && inoise && rgb_out && workspace, "null argument");
   SX_REQUIRE(noise_batch == 1 || noise_batch == B, "noise batch %d must be 1 or B=%d", noise_batch, B);
   SX_REQUIRE(start_conv >= 0 && start_conv < 2 * g->num_blocks, "start_conv=%d out of range", start_conv);
   SX_REQUIRE(!(save_cache && (B != 1 || start_conv != 0)), "save_cache needs B == 1 and start_conv == 0");

@@ -444,6 +444,39 @@ def test_native_preprocess_matches_torchvision(dev, size):
         sx.make_classifier("mobilenet", model, size).use_native_preprocess(True)
 
 
+def test_edge_cases_empty_and_ragged(dev):
+    """empty batches are no-ops, a single latent works (min == max: every shift is 0), odd batch sizes and coordinate
+    subsets that straddle conv boundaries are handled."""
+    m = sx.Conv2DMod(16, 8, 3).to(dev)
+    out = m(torch.zeros(0, 16, 8, 8, device=dev), torch.zeros(0, 16, device=dev))
+    assert out.shape == (0, 8, 8, 8)
+    assert sx.modules.upsample2x(torch.zeros(0, 3, 4, 4, device=dev)).shape == (0, 3, 8, 8)
+    sd = synthetic.make_generator_state(16, seed=3, network_capacity=4)
+    G = g_module(sd, 16, 4, dev)
+    noise = synthetic.make_noise(16, 3).to(dev)
+    assert G(torch.zeros(0, G.num_layers, 514, device=dev), noise).shape == (0, 3, 16, 16)
+
+    class Mean:
+        def classify_images(self, x):
+            return torch.stack([x[:, 0, 2, 3], x[:, 1, 5, 1]], 1)
+
+    lat = synthetic.make_latents(1, 3).to(dev)
+    r = sx.attfind_sweep(G, Mean(), lat, noise, max_batch=7)          # odd max_batch -> rounded down to 6
+    assert r["style_change"].shape == (1, 2, G.num_style_coords, 2)
+    assert float(r["style_change"].abs().max()) == 0.0               # one latent: minima == maxima == its own coords
+    lat3 = synthetic.make_latents(3, 3).to(dev)
+    S = G.num_style_coords
+    sub = [0, 31, 32, 63, 64, S - 1]                                  # straddles conv1/conv2 and block boundaries
+    full = sx.attfind_sweep(G, Mean(), lat3, noise, max_batch=16)
+    part = sx.attfind_sweep(G, Mean(), lat3, noise, max_batch=4, sindices=sub)
+    assert torch.equal(part["style_change"][:, :, sub], full["style_change"][:, :, sub])
+    mask = torch.ones(S, dtype=torch.bool)
+    mask[sub] = False
+    assert float(part["style_change"][:, :, mask].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        sx.attfind_sweep(G, Mean(), lat3, noise, minmax=(torch.zeros(3, device=dev), torch.zeros(3, device=dev)))
+
+
 def test_native_launches_counted(dev):
     before = _native.launch_count()
     sx.modules.upsample2x(torch.zeros(1, 1, 4, 4, device=dev))
