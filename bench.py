@@ -328,6 +328,9 @@ def run_ours(args):
     launches0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ncu_range = bool(os.environ.get("SX_NCU_RANGE"))   # `ncu --profile-from-start off`: capture the timed region only
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     evals = 0
     for k in range(args.steps):
@@ -335,6 +338,8 @@ def run_ours(args):
         evals += n
     e1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     launches = _native.launch_count() - launches0
     prof = _native.profile_collect()

@@ -400,11 +400,60 @@ static int selftest_case(int B, int Ci, int Co, int H, float* max_err) {
   return rc;
 }
 
+// fused-upsample conv (low-resolution input, upsample inside the kernel) vs upsample kernel + plain halo conv.
+// Inputs are coarse (multiples of 1/64), so every bilinear sum is exact in fp32 and both paths round the same
+// values to bf16: the two outputs must agree to the last bit.
+static int selftest_ups_case(int B, int Ci, int Co, int H, float* max_err) {
+  const int Hs = H / 2;
+  const size_t nlow = (size_t)B * Hs * Hs * Ci, nfull = (size_t)B * H * H * Ci, nw = (size_t)Co * 9 * Ci, no = (size_t)B * H * H * Co;
+  std::vector<__nv_bfloat16> hx(nlow), hw(nw), oa(no), ob(no);
+  uint32_t seed = 777u + B * 7 + Ci * 13 + Co * 17 + H;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : hx) v = __float2bfloat16_rn(roundf(rnd() * 64.f) / 64.f);
+  for (auto& v : hw) v = __float2bfloat16_rn(rnd() * 0.2f);
+  __nv_bfloat16 *dlow, *dfull, *dw, *da, *db;
+  SX_CUDA(cudaMalloc(&dlow, nlow * 2));
+  SX_CUDA(cudaMalloc(&dfull, nfull * 2));
+  SX_CUDA(cudaMalloc(&dw, nw * 2));
+  SX_CUDA(cudaMalloc(&da, no * 2));
+  SX_CUDA(cudaMalloc(&db, no * 2));
+  SX_CUDA(cudaMemcpy(dlow, hx.data(), nlow * 2, cudaMemcpyHostToDevice));
+  SX_CUDA(cudaMemcpy(dw, hw.data(), nw * 2, cudaMemcpyHostToDevice));
+  SX_CUDA(cudaMemset(da, 0xFF, no * 2));
+  SX_CUDA(cudaMemset(db, 0x7F, no * 2));
+  ConvEpilogue ep{};
+  ep.act = 1;
+  int rc = launch_upsample2x_modulate<__nv_bfloat16>(dlow, (long long)Hs * Hs * Ci, nullptr, 0, dfull, B, Hs, Hs, Ci, nullptr);
+  bool handled = false;
+  ep.out = da;
+  if (rc == SX_OK) rc = tc::launch_conv_halo(dfull, dw, B, Ci, Co, H, H, ep, nullptr, &handled);
+  if (rc == SX_OK && !handled) rc = fail(SX_EUNSUPPORTED, "selftest(ups): halo kernel does not cover Ci=%d Co=%d H=%d", Ci, Co, H);
+  ep.out = db;
+  if (rc == SX_OK) rc = tc::launch_conv_halo_ups(dlow, dw, B, Ci, Co, H, H, ep, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc == SX_OK && e != cudaSuccess) rc = fail(SX_ECUDA, "selftest(ups) B=%d Ci=%d Co=%d H=%d: %s", B, Ci, Co, H, cudaGetErrorString(e));
+  if (rc == SX_OK) {
+    cudaMemcpy(oa.data(), da, no * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ob.data(), db, no * 2, cudaMemcpyDeviceToHost);
+    float m = 0.f;
+    for (size_t i = 0; i < no; ++i) {
+      const float d = fabsf(__bfloat162float(oa[i]) - __bfloat162float(ob[i]));
+      if (!(d <= m)) m = d;
+    }
+    if (m != 0.f) rc = fail(SX_ECUDA, "selftest(ups) B=%d Ci=%d Co=%d H=%d: fused-upsample conv differs from upsample + conv by %g", B, Ci, Co, H, m);
+    if (!(m <= *max_err)) *max_err = m;
+  }
+  cudaFree(dlow); cudaFree(dfull); cudaFree(dw); cudaFree(da); cudaFree(db);
+  return rc;
+}
+
 int sx_tc_selftest(float tol, float* max_err_out) {
   SX_TRY(sx_device_check());
   float max_err = 0.f;
   const int cases[][4] = {{2, 64, 64, 16}, {3, 32, 32, 8}, {5, 128, 256, 4}, {1, 64, 32, 128}, {2, 512, 512, 8}, {1, 64, 128, 32}};
   for (auto& c : cases) SX_TRY(selftest_case(c[0], c[1], c[2], c[3], &max_err));
+  const int ups_cases[][4] = {{2, 64, 32, 64}, {3, 64, 32, 32}, {1, 128, 64, 32}, {2, 256, 128, 32}, {1, 64, 64, 64}};
+  for (auto& c : ups_cases) SX_TRY(selftest_ups_case(c[0], c[1], c[2], c[3], &max_err));
   if (max_err_out) *max_err_out = max_err;
   if (!(max_err <= tol)) return fail(SX_ECUDA, "tcgen05 selftest: max-abs error %g > tol %g", max_err, tol);
   return SX_OK;

@@ -37,9 +37,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
+// fused-upsample variant (UPS): the conv input is the LOW-RESOLUTION tensor; a 10 x 6 pixel source box per channel chunk
+// is TMA-loaded (un-swizzled) into its own ring and four producer warps write the bilinearly upsampled 18 x 10 halo box
+// into the swizzled A stage (see the producer branch of the kernel).
+constexpr int UPS_SRC_W = HALO_W / 2 + 1, UPS_SRC_H = HALO_H / 2 + 1;   // 6 x 10 source pixels
+constexpr int UPS_S_STAGES = 2;
+constexpr int UPS_THREADS = 128;
+
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS = false>
 struct HaloCfg {
   static constexpr int kRowBytes = BLOCK_K * 2;
+  static constexpr int kThreads = NUM_THREADS + (UPS ? UPS_THREADS : 0);
+  static constexpr int kSrcBytes = UPS_SRC_W * UPS_SRC_H * kRowBytes;   // one source box (7680 B at BLOCK_K = 64)
+  static constexpr int kSrcRegion = UPS ? UPS_S_STAGES * kSrcBytes : 0;
   static constexpr int kATx = HALO_ROWS * kRowBytes;              // bytes one halo box delivers
   static constexpr int kABytes = (kATx + 1023) / 1024 * 1024;     // stage stride (keeps every stage 1024 B aligned)
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;           // weights of one (channel chunk, tap)
@@ -47,7 +57,7 @@ struct HaloCfg {
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
   __host__ __device__ static size_t b_region(int num_b_tiles) { return (size_t)(RESIDENT_B ? num_b_tiles : B_STAGES) * kBBytes; }
   static size_t smem_bytes(int num_b_tiles) {
-    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + 256 + (size_t)(2 + 4 + 6) * BLOCK_N * sizeof(float);
+    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + 256 + (size_t)(2 + 4 + 6) * BLOCK_N * sizeof(float) + kSrcRegion;
   }
 };
 
@@ -66,11 +76,11 @@ struct ConvHaloParams {
 template <int BLOCK_N, int BLOCK_K>
 constexpr int halo_min_ctas() { return BLOCK_N == 32 ? 2 : 1; }   // 2 CTAs/SM where smem allows it; 3 (96 regs, spills) measured slower
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
-__global__ void __launch_bounds__(NUM_THREADS, halo_min_ctas<BLOCK_N, BLOCK_K>()) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                   const __grid_constant__ CUtensorMap tmap_b,
-                                                                   const ConvHaloParams p) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS>
+__global__ void __launch_bounds__(NUM_THREADS + (UPS ? UPS_THREADS : 0), halo_min_ctas<BLOCK_N, BLOCK_K>())
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvHaloParams p) {
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS>;
+  static_assert(!UPS || BLOCK_K == 64, "the fused-upsample producer writes the SWIZZLE_128B layout");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -82,13 +92,16 @@ __global__ void __launch_bounds__(NUM_THREADS, halo_min_ctas<BLOCK_N, BLOCK_K>()
   uint64_t* b_empty = b_full + B_STAGES;
   uint64_t* tmem_full = b_empty + B_STAGES;       // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  static_assert((2 * A_STAGES + 2 * B_STAGES + 4) * 8 + 8 <= 256, "barrier block overflow");
+  uint64_t* s_full = tmem_empty + 2;              // [UPS_S_STAGES]  (UPS only) source box landed
+  uint64_t* s_empty = s_full + UPS_S_STAGES;      // [UPS_S_STAGES]  (UPS only) producers are done with the source box
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_empty + UPS_S_STAGES);
+  static_assert((2 * A_STAGES + 2 * B_STAGES + 4 + 2 * UPS_S_STAGES) * 8 + 8 <= 256, "barrier block overflow");
   float* s_nw = reinterpret_cast<float*>(after + 256);
   float* s_nb = s_nw + BLOCK_N;
   float* s_d = s_nb + BLOCK_N;            // [2][BLOCK_N] demod coefficients of the tile's sample (per accumulator slot)
   float* s_m = s_d + 2 * BLOCK_N;         // [2][BLOCK_N] next-layer (style+1)
   float* s_rgbw = s_m + 2 * BLOCK_N;      // [2][3][BLOCK_N] fused-ToRGB weights of the tile's sample
+  uint8_t* smem_src = reinterpret_cast<uint8_t*>(s_rgbw + 6 * BLOCK_N);   // (UPS only) [UPS_S_STAGES][10][6][BLOCK_K] bf16
 
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,9 +115,10 @@ __global__ void __launch_bounds__(NUM_THREADS, halo_min_ctas<BLOCK_N, BLOCK_K>()
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], UPS ? UPS_THREADS : 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    if (UPS) for (int s = 0; s < UPS_S_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], UPS_THREADS); }
     fence_barrier_init();
   } else if (warp_id == 1) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
@@ -132,14 +146,23 @@ __global__ void __launch_bounds__(NUM_THREADS, halo_min_ctas<BLOCK_N, BLOCK_K>()
         const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
         const int x0 = tx * HALO_BW, y0 = ty * HALO_BH;
         for (int chunk = 0; chunk < p.kchunks; ++chunk) {
-          mbar_wait(&a_empty[as], aph ^ 1, 10);
-          if (dbg & 4) {
-            mbar_arrive(&a_full[as]);
+          if (UPS) {
+            // low-resolution source box of the halo box: rows y0/2-1 .. y0/2+8, columns x0/2-1 .. x0/2+4 (zero-filled
+            // outside the image; the producers clamp instead, like torch's bilinear kernel)
+            mbar_wait(&s_empty[as], aph ^ 1, 10);
+            mbar_arrive_expect_tx(&s_full[as], Cfg::kSrcBytes);
+            tma_load_4d(smem_src + as * Cfg::kSrcBytes, &tmap_a, &s_full[as], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
+            if (++as == UPS_S_STAGES) { as = 0; aph ^= 1; }
           } else {
-            mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
-            tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+            mbar_wait(&a_empty[as], aph ^ 1, 10);
+            if (dbg & 4) {
+              mbar_arrive(&a_full[as]);
+            } else {
+              mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
+              tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+            }
+            if (++as == A_STAGES) { as = 0; aph ^= 1; }
           }
-          if (++as == A_STAGES) { as = 0; aph ^= 1; }
           if (!RESIDENT_B) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[bs], bph ^ 1, 11);
@@ -203,6 +226,87 @@ __global__ void __launch_bounds__(NUM_THREADS, halo_min_ctas<BLOCK_N, BLOCK_K>()
       }
     }
     __syncwarp();
+  } else if (UPS && warp_id >= 6) {
+    // ===================== fused bilinear 2x upsample: A-operand producers (warps 6..9) =====================
+    // out halo pixel (hy, hx) <-> image pixel (y0-1+hy, x0-1+hx); y0, x0 are even, so halo rows (2k, 2k+1) interpolate
+    // source-box rows (k, k+1) with weights (.75,.25) / (.25,.75) (align_corners=False, scale 2: src = o/2 - 0.25),
+    // and likewise for columns.  Source indices are clamped to the image (torch's border rule); halo pixels outside
+    // the image are the conv's zero padding.  Thread = one 16-byte channel group x one column pair x one third of
+    // the rows; horizontal pass per source row, then the vertical pass, all in fp32, one rounding to bf16.
+    const int pt = threadIdx.x - NUM_THREADS;   // 0..127
+    const int cg = pt & 7;
+    const int unit = pt >> 3;                   // 0..15; unit 15 has no work
+    const int j = unit % 5;                     // halo columns 2j, 2j+1 <- source columns j, j+1
+    const int seg = unit / 5;                   // halo rows 6seg .. 6seg+5 <- source rows 3seg .. 3seg+3
+    int as = 0, ss = 0;
+    uint32_t aph = 0, sph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int b = tile >> p.tpb_shift;
+      const int tr = tile - (b << p.tpb_shift);
+      const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
+      const bool left = tx == 0, right = tx == p.tiles_x - 1, top = ty == 0, bottom = ty == p.tiles_y - 1;
+      const int lo_c = left ? 1 : 0, hi_c = right ? UPS_SRC_W - 2 : UPS_SRC_W - 1;
+      const int lo_r = top ? 1 : 0, hi_r = bottom ? UPS_SRC_H - 2 : UPS_SRC_H - 1;
+      const int c0 = min(max(j, lo_c), hi_c), c1 = min(max(j + 1, lo_c), hi_c);
+      const bool zero_e = left && j == 0;        // halo column 0 is outside the image
+      const bool zero_o = right && j == 4;       // halo column 9 is outside the image
+      for (int chunk = 0; chunk < p.kchunks; ++chunk) {
+        mbar_wait(&s_full[ss], sph, 17);
+        mbar_wait(&a_empty[as], aph ^ 1, 18);
+        if (seg < 3) {
+          const uint8_t* src = smem_src + ss * Cfg::kSrcBytes + cg * 16;
+          uint8_t* dst = smem_a + as * Cfg::kABytes;
+          float he0[8], ho0[8], he1[8], ho1[8];
+          auto hrow = [&](int r, float* he, float* ho) {
+            const int rr = min(max(r, lo_r), hi_r);
+            float a[8], c[8];
+            unpack(*reinterpret_cast<const uint4*>(src + (rr * UPS_SRC_W + c0) * Cfg::kRowBytes), a);
+            unpack(*reinterpret_cast<const uint4*>(src + (rr * UPS_SRC_W + c1) * Cfg::kRowBytes), c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              he[k] = fmaf(0.25f, c[k], 0.75f * a[k]);   // odd image column 2m+1
+              ho[k] = fmaf(0.75f, c[k], 0.25f * a[k]);   // even image column 2m+2
+            }
+          };
+          auto put = [&](int hy, int hx, const float* v, bool zero) {
+            const int pix = hy * HALO_W + hx;
+            uint4 pk;
+            if (zero) pk = make_uint4(0u, 0u, 0u, 0u);
+            else pack(v, pk);
+            *reinterpret_cast<uint4*>(dst + pix * Cfg::kRowBytes + ((cg ^ (pix & 7)) << 4)) = pk;
+          };
+          hrow(3 * seg, he0, ho0);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int k = 3 * seg + i;
+            hrow(k + 1, he1, ho1);
+            const bool zt = top && k == 0;        // halo row 0 is outside the image
+            const bool zb = bottom && k == 8;     // halo row 17 is outside the image
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.25f, he1[q], 0.75f * he0[q]);
+            put(2 * k, 2 * j, v, zt || zero_e);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.25f, ho1[q], 0.75f * ho0[q]);
+            put(2 * k, 2 * j + 1, v, zt || zero_o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.75f, he1[q], 0.25f * he0[q]);
+            put(2 * k + 1, 2 * j, v, zb || zero_e);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.75f, ho1[q], 0.25f * ho0[q]);
+            put(2 * k + 1, 2 * j + 1, v, zb || zero_o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { he0[q] = he1[q]; ho0[q] = ho1[q]; }
+          }
+        }
+        // generic-proxy writes -> visible to the async proxy (tcgen05.mma reads shared memory through it)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&a_full[as]);
+        mbar_arrive(&s_empty[ss]);
+        if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        if (++ss == UPS_S_STAGES) { ss = 0; sph ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const ConvEpilogue& ep = p.ep;
@@ -370,29 +474,32 @@ inline bool halo_shape_supported(int Ci, int Co, int H, int W) {
   return true;
 }
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS>
 int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream);
 
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
 int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true>(x, wk, p, stream);
-  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false>(x, wk, p, stream);
+  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false>(x, wk, p, stream);
+  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false>(x, wk, p, stream);
 }
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB>
+// x: the conv input [B,H,W,Ci] -- or, for UPS, the low-resolution tensor [B,H/2,W/2,Ci] the kernel upsamples itself
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS>
 int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B>;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS>;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   const CUtensorMapSwizzle swz = BLOCK_K == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap ta, tb;
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)p.Ci, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-    cuuint64_t gstr[3] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)p.W * p.Ci * 2, (cuuint64_t)p.H * p.W * p.Ci * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
+    const int IH = UPS ? p.H / 2 : p.H, IW = UPS ? p.W / 2 : p.W;
+    cuuint64_t gdim[4] = {(cuuint64_t)p.Ci, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)p.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)IW * p.Ci * 2, (cuuint64_t)IH * IW * p.Ci * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(UPS ? UPS_SRC_W : HALO_W), (cuuint32_t)(UPS ? UPS_SRC_H : HALO_H), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, UPS ? CU_TENSOR_MAP_SWIZZLE_NONE : swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
   }
   {
@@ -405,7 +512,7 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB>;
+  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS>;
   const size_t smem = Cfg::smem_bytes(p.num_b_tiles);
   if (smem > 227 * 1024) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -424,7 +531,7 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
     SX_CUDA(cudaFuncGetAttributes(&fa, kern));
     const int regs = (fa.numRegs + 7) / 8 * 8;
     const int occ_smem = (int)((227 * 1024) / (smem + 1024));
-    const int occ_regs = 65536 / (regs * NUM_THREADS);
+    const int occ_regs = 65536 / (regs * Cfg::kThreads);
     const int occ_tmem = 512 / Cfg::kTmemCols;
     int occ = occ_smem < occ_regs ? occ_smem : occ_regs;
     occ = occ < occ_tmem ? occ : occ_tmem;
@@ -433,17 +540,12 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
   int grid_x = occ_cached * num_sms();
   if (grid_x > p.num_tiles) grid_x = p.num_tiles;
   dim3 grid((unsigned)grid_x, (unsigned)(p.Co / BLOCK_N));
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, p);
+  kern<<<grid, Cfg::kThreads, smem, stream>>>(ta, tb, p);
   SX_CHECK_LAUNCH();
   return SX_OK;
 }
 
-// returns SX_EUNSUPPORTED (without setting an error the caller must report) when the halo kernel does not cover the shape
-inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int B, int Ci, int Co, int H, int W,
-                            const ConvEpilogue& ep, cudaStream_t stream, bool* handled) {
-  *handled = false;
-  if (!halo_shape_supported(Ci, Co, H, W) || B == 0) return SX_OK;
-  const int bk = Ci % 64 == 0 ? 64 : 32;
+inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int bk, const ConvEpilogue& ep) {
   ConvHaloParams p;
   p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
   p.tiles_x = W / HALO_BW; p.tiles_y = H / HALO_BH;
@@ -457,6 +559,16 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   p.kchunks = Ci / bk;
   p.num_b_tiles = 9 * p.kchunks;
   p.ep = ep;
+  return p;
+}
+
+// *handled = false (and SX_OK) when the halo kernel does not cover the shape
+inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int B, int Ci, int Co, int H, int W,
+                            const ConvEpilogue& ep, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (!halo_shape_supported(Ci, Co, H, W) || B == 0) return SX_OK;
+  const int bk = Ci % 64 == 0 ? 64 : 32;
+  const ConvHaloParams p = make_halo_params(B, Ci, Co, H, W, bk, ep);
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
   const bool resident = weight_bytes <= 80 * 1024;
   *handled = true;
@@ -469,6 +581,27 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 3, 4, false>(x, wk, p, stream);
   *handled = false;
   return SX_OK;
+}
+
+// Fused-upsample variant: xlow is the LOW-RESOLUTION input [B,H/2,W/2,Ci] (already modulated); H, W are the conv's
+// (output) sizes.  The upsampled tensor is never written to memory: 4x less input traffic and no upsample kernel.
+inline bool halo_ups_supported(int Ci, int Co, int H, int W) {
+  if (!halo_shape_supported(Ci, Co, H, W) || Ci % 64 != 0 || H < 32) return false;
+  const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
+  if (Co == 32) return weight_bytes <= 80 * 1024;
+  return Co == 64 || Co == 128;
+}
+inline int launch_conv_halo_ups(const __nv_bfloat16* xlow, const __nv_bfloat16* wk, int B, int Ci, int Co, int H, int W,
+                                const ConvEpilogue& ep, cudaStream_t stream) {
+  if (!halo_ups_supported(Ci, Co, H, W)) return fail(SX_EUNSUPPORTED, "conv_tc_halo(ups): unsupported shape Ci=%d Co=%d H=%d", Ci, Co, H);
+  if (ep.rgb_style) return fail(SX_EINVAL, "conv_tc_halo(ups): fused ToRGB is a conv2 feature");
+  if (B == 0) return SX_OK;
+  const ConvHaloParams p = make_halo_params(B, Ci, Co, H, W, 64, ep);
+  const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
+  if (Co == 32) return launch_conv_halo_cfg2<32, 64, 2, 2, true, false, true>(xlow, wk, p, stream);
+  if (Co == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true>(xlow, wk, p, stream);
+  if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true>(xlow, wk, p, stream);
+  return launch_conv_halo_cfg2<128, 64, 3, 4, false, false, true>(xlow, wk, p, stream);
 }
 
 // bf16 Conv2DMod dispatch: the halo-reusing persistent kernel where it applies, the per-tap kernel otherwise.

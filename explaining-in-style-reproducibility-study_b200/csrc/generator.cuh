@@ -208,6 +208,19 @@ inline int run_conv<__nv_bfloat16>(const sx_generator* g, int conv_idx, const __
 }
 
 template <typename T>
+inline int run_conv_ups(const sx_generator* g, int conv_idx, const T* xlow, int B, int Ci, int Co, int H, const ConvEpilogue& ep,
+                        cudaStream_t st);
+template <>
+inline int run_conv_ups<float>(const sx_generator*, int, const float*, int, int, int, int, const ConvEpilogue&, cudaStream_t) {
+  return fail(SX_EUNSUPPORTED, "internal: the fused-upsample conv is a bf16 kernel");
+}
+template <>
+inline int run_conv_ups<__nv_bfloat16>(const sx_generator* g, int conv_idx, const __nv_bfloat16* xlow, int B, int Ci, int Co, int H,
+                                       const ConvEpilogue& ep, cudaStream_t st) {
+  return tc::launch_conv_halo_ups(xlow, g->conv[conv_idx].wbf, B, Ci, Co, H, H, ep, st);
+}
+
+template <typename T>
 int generator_forward_t(sx_generator* g, const float* styles, const float* inoise, int noise_batch, float* rgb_out, int B,
                         int start_conv, int save_cache, uint8_t* ws, const GenWorkspace& L, cudaStream_t st) {
   const int nb = g->num_blocks, row = g->style_row;
@@ -246,6 +259,19 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
   }
 
   const int start_block = start_conv / 2;
+  // ToRGB is fused into the conv2 epilogue when the kernel has the whole channel row of a pixel in one thread
+  // and one sample per M tile: bf16 path, Co <= 256, H >= 16.
+  static const bool fuse_off = getenv("SX_DISABLE_RGB_FUSION") != nullptr;
+  auto rgb_fused = [&](int l) { return !fuse_off && std::is_same<T, __nv_bfloat16>::value && g->co[l] <= 256 && (4 << l) >= 16; };
+  // The bilinear 2x upsample in front of conv1 is fused into the conv kernel (its A-operand producers) where the
+  // halo kernel covers the shape: the previous block's conv2 then stores its output already modulated by this block's
+  // style1 (its ToRGB must be fused, because nothing else sees the un-modulated tensor) and the upsampled tensor is
+  // never materialised.  The clean-prefix cache of such a conv1 holds the LOW-RESOLUTION raw tensor.
+  static const bool ups_off = getenv("SX_DISABLE_UPS_FUSION") != nullptr;
+  auto ups_fused = [&](int l) {
+    return !ups_off && std::is_same<T, __nv_bfloat16>::value && l >= 1 && rgb_fused(l - 1) &&
+           tc::halo_ups_supported(g->ci[l], g->co[l], 4 << l, 4 << l);
+  };
   const float* prev_rgb = nullptr;  // rgb of the previous block, [Bp,3,H/2,H/2]
   long long prev_bstride = 0;
   if (start_block > 0) {
@@ -261,7 +287,26 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
     const bool run_conv1 = start_conv <= 2 * l;
     ConvEpilogue ep{};
     ep.noise = inoise; ep.noise_batch = noise_batch; ep.noise_size = S; ep.act = 1; ep.dcoef_stride = g->demod_row;
-    if (run_conv1) {
+    const bool ups = ups_fused(l);
+    if (run_conv1 && ups) {
+      // ---- conv1 with the upsample fused: its input is the low-resolution tensor modulated by (style1 + 1)
+      const long long HWs = HW / 4;
+      const T* xlow = y2;   // written (modulated) by the previous block's conv2 epilogue
+      if (l == start_block) {
+        ProfScope ps(32, 0, (double)sizeof(T) * B * HWs * ci, st);
+        SX_TRY(launch_modulate<T>(cache_in(2 * l), 0, styles + g->soff1[l], row, xin, B, HWs, ci, st));
+        xlow = xin;
+      }
+      ep.dcoef = dcoef + g->doff1[l];
+      ep.noise_w = g->conv[2 * l].noise_w; ep.noise_b = g->conv[2 * l].noise_b;
+      ep.next_style = styles + g->soff2[l]; ep.next_style_stride = row;
+      ep.out = y1m; ep.out_nchw_f32 = 0;
+      ep.out_raw = save_cache ? cache_in(2 * l + 1) : nullptr;
+      {
+        ProfScope ps(2 * l, 2.0 * 9 * ci * co * (double)HW * B, 2.0 * B * (HWs * ci + HW * co), st);
+        SX_TRY(run_conv_ups<T>(g, 2 * l, xlow, B, ci, co, H, ep, st));
+      }
+    } else if (run_conv1) {
       // ---- input of conv1, modulated by (style1 + 1)
       if (l == start_block) {
         const T* src = (l == 0) ? x0 : cache_in(2 * l);
@@ -294,14 +339,16 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
     float* rgb_dst = (l == nb - 1) ? rgb_out : ((l & 1) ? rgb_pong : rgb_ping);
     if (l != nb - 1 && (size_t)B * 3 * HW * 4 > ((l & 1) ? (L.total - L.rgb_b) : (L.rgb_b - L.rgb_a)))
       return fail(SX_ENOMEM, "internal: rgb scratch too small");
-    // ToRGB is fused into the conv2 epilogue when the kernel has the whole channel row of a pixel in one thread
-    // and one sample per M tile: bf16 path, Co <= 256, H >= 16.
-    static const bool fuse_off = getenv("SX_DISABLE_RGB_FUSION") != nullptr;
-    const bool fuse_rgb = !fuse_off && std::is_same<T, __nv_bfloat16>::value && co <= 256 && H >= 16;
+    const bool fuse_rgb = rgb_fused(l);
+    const bool next_ups = l + 1 < nb && ups_fused(l + 1);
     ep.dcoef = dcoef + g->doff2[l];
     ep.noise_w = g->conv[2 * l + 1].noise_w; ep.noise_b = g->conv[2 * l + 1].noise_b;
     ep.next_style = nullptr; ep.next_style_stride = 0;
     ep.out = y2; ep.out_raw = nullptr;
+    if (next_ups) {   // y2 leaves this conv modulated for the next block's conv1; the raw copy feeds the prefix cache
+      ep.next_style = styles + g->soff1[l + 1]; ep.next_style_stride = row;
+      ep.out_raw = save_cache ? cache_in(2 * l + 2) : nullptr;
+    }
     if (fuse_rgb) {
       if (prev_rgb) {
         ProfScope ps(37, 0, (double)B * HW * 15, st);
