@@ -344,31 +344,41 @@ int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const fl
 // neighbourhood {i-1, i, i+1} with weights (5,10,1)/16 for even and (1,10,5)/16 for odd output coordinates
 // (9 loads + 9 FMAs per channel); pixels whose neighbourhood touches the border (index clamping of the upsample,
 // reflect padding of the blur) take the generic two-step evaluation.
-__global__ void __launch_bounds__(256) rgb_prev_up_blur_kernel(const float* __restrict__ prev, long long prev_bstride,
+// One thread = one 2x2 output quad (all 3 channels): the four pixels share the low-res neighbourhood, so 27 loads
+// serve 12 outputs (the one-pixel-per-thread version issued 27 per 3 and was LSU-bound at 22 ms per sweep step).
+__global__ void __launch_bounds__(128) rgb_prev_up_blur_kernel(const float* __restrict__ prev, long long prev_bstride,
                                                                float* __restrict__ rgb, int h, int w) {
   const int H = 2 * h, W = 2 * w;
   const int b = blockIdx.z;
-  const int y = blockIdx.y;
+  const int i = blockIdx.y;
   const float* pp = prev + (long long)b * prev_bstride;
   float* dst = rgb + (long long)b * 3 * H * W;
-  const int i = y >> 1;
   const bool yint = i >= 1 && i <= h - 2;
-  const float wy0 = (y & 1) ? 0.0625f : 0.3125f, wy2 = (y & 1) ? 0.3125f : 0.0625f;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
-    const int j = x >> 1;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < w; j += gridDim.x * blockDim.x) {
     if (yint && j >= 1 && j <= w - 2) {
-      const float wx0 = (x & 1) ? 0.0625f : 0.3125f, wx2 = (x & 1) ? 0.3125f : 0.0625f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* p = pp + (size_t)c * h * w + (size_t)(i - 1) * w + (j - 1);
-        const float r0 = wx0 * __ldg(p) + 0.625f * __ldg(p + 1) + wx2 * __ldg(p + 2);
-        const float r1 = wx0 * __ldg(p + w) + 0.625f * __ldg(p + w + 1) + wx2 * __ldg(p + w + 2);
-        const float r2 = wx0 * __ldg(p + 2 * w) + 0.625f * __ldg(p + 2 * w + 1) + wx2 * __ldg(p + 2 * w + 2);
-        dst[((size_t)c * H + y) * W + x] = wy0 * r0 + 0.625f * r1 + wy2 * r2;
+        float re[3], ro[3];   // even / odd output column of the three low-res rows
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float p0 = __ldg(p + r * w), p1 = __ldg(p + r * w + 1), p2 = __ldg(p + r * w + 2);
+          re[r] = 0.3125f * p0 + 0.625f * p1 + 0.0625f * p2;
+          ro[r] = 0.0625f * p0 + 0.625f * p1 + 0.3125f * p2;
+        }
+        float* d = dst + ((size_t)c * H + 2 * i) * W + 2 * j;
+        *reinterpret_cast<float2*>(d) = make_float2(0.3125f * re[0] + 0.625f * re[1] + 0.0625f * re[2],
+                                                    0.3125f * ro[0] + 0.625f * ro[1] + 0.0625f * ro[2]);
+        *reinterpret_cast<float2*>(d + W) = make_float2(0.0625f * re[0] + 0.625f * re[1] + 0.3125f * re[2],
+                                                        0.0625f * ro[0] + 0.625f * ro[1] + 0.3125f * ro[2]);
       }
     } else {
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int y = 2 * i + (q >> 1), x = 2 * j + (q & 1);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) dst[((size_t)c * H + y) * W + x] = up2_blur(pp + (size_t)c * h * w, nullptr, h, w, y, x);
+        for (int c = 0; c < 3; ++c) dst[((size_t)c * H + y) * W + x] = up2_blur(pp + (size_t)c * h * w, nullptr, h, w, y, x);
+      }
     }
   }
 }
@@ -376,8 +386,9 @@ __global__ void __launch_bounds__(256) rgb_prev_up_blur_kernel(const float* __re
 inline int launch_rgb_prev_up_blur(const float* prev, long long prev_bstride, float* rgb, int B, int H, int W, cudaStream_t st) {
   if (B == 0) return SX_OK;
   SX_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 4 && W >= 4, "rgb_prev: bad size %dx%d", H, W);
-  const int threads = W >= 256 ? 256 : (W >= 128 ? 128 : (W >= 64 ? 64 : 32));
-  dim3 grid((W + threads - 1) / threads, H, B);
+  const int w = W / 2;
+  const int threads = w >= 128 ? 128 : (w >= 64 ? 64 : 32);
+  dim3 grid((w + threads - 1) / threads, H / 2, B);
   SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "rgb_prev: grid too large");
   rgb_prev_up_blur_kernel<<<grid, threads, 0, st>>>(prev, prev_bstride, rgb, H / 2, W / 2);
   SX_CHECK_LAUNCH();

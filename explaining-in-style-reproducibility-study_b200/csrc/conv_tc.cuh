@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
                                                               const ConvTcParams p) {
   using Cfg = TcConfig<BLOCK_N, BLOCK_K, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ array (not an integer round trip) keeps the shared address space known to the
+  // compiler: the table / source-box accesses below compile to LDS/STS instead of generic LD/ST (ncu: long_scoreboard)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);

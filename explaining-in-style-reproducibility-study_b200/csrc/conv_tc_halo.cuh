@@ -82,7 +82,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS>;
   static_assert(!UPS || BLOCK_K == 64, "the fused-upsample producer writes the SWIZZLE_128B layout");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ array (not an integer round trip) keeps the shared address space known to the
+  // compiler: the table / source-box accesses below compile to LDS/STS instead of generic LD/ST (ncu: long_scoreboard)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + A_STAGES * Cfg::kABytes;
   uint8_t* after = smem_b + Cfg::b_region(p.num_b_tiles);
