@@ -83,7 +83,7 @@ class _Wrapper:
         self.native_preprocess = on
         return self
 
-    def _native_pre(self, images: torch.Tensor) -> torch.Tensor:
+    def _native_pre(self, images: torch.Tensor, s2d: bool = False) -> torch.Tensor:
         import ctypes
         from . import _native as N
 
@@ -94,18 +94,28 @@ class _Wrapper:
         if c != 3:
             raise ValueError("native preprocessing expects 3-channel images")
         d = self.resnet_dim
-        out = torch.empty((b, 3, d, d), device=x.device, dtype=self.compute_dtype, memory_format=torch.channels_last)
         if self.compute_dtype not in (torch.float32, torch.bfloat16):
             raise NotImplementedError("native preprocessing writes fp32 or bf16")
         mean = (ctypes.c_float * 3)(*_MEAN)
         std = (ctypes.c_float * 3)(*_STD)
-        N.check(N.lib().sx_resize_aa_normalize(x.data_ptr(), out.data_ptr(), 1 if self.compute_dtype == torch.bfloat16 else 0, b,
-                                               h, w, d, d, 1 if self.normalize else 0, mean, std, N.stream_ptr()),
+        bf16 = 1 if self.compute_dtype == torch.bfloat16 else 0
+        if s2d:   # the space-to-depth network input of the re-expressed stem (FusedResNetInference.stem_s2d)
+            out = torch.empty((b, 16, d // 2 + 3, d // 2 + 3), device=x.device, dtype=self.compute_dtype,
+                              memory_format=torch.channels_last)
+            N.check(N.lib().sx_resize_aa_normalize_s2d(x.data_ptr(), out.data_ptr(), bf16, b, h, w, d, d,
+                                                       1 if self.normalize else 0, mean, std, N.stream_ptr()),
+                    "sx_resize_aa_normalize_s2d")
+            return out
+        out = torch.empty((b, 3, d, d), device=x.device, dtype=self.compute_dtype, memory_format=torch.channels_last)
+        N.check(N.lib().sx_resize_aa_normalize(x.data_ptr(), out.data_ptr(), bf16, b, h, w, d, d,
+                                               1 if self.normalize else 0, mean, std, N.stream_ptr()),
                 "sx_resize_aa_normalize")
         return out
 
     def classify_images(self, images) -> torch.Tensor:
         if self.native_preprocess and isinstance(images, torch.Tensor):
+            if self.fused is not None and self.fused.stem_s2d is not None:
+                return self.fused(self._native_pre(images, s2d=True), s2d_input=True).float()
             x = self._native_pre(images)
             return (self.fused(x) if self.fused is not None else self.model(x)).float()
         x = self.preprocess(images)
@@ -139,6 +149,29 @@ class FusedResNetInference:
                 self.blocks.append((self._fold(blk.conv1, blk.bn1), self._fold(blk.conv2, blk.bn2), ds))
         self.fc_w = model.fc.weight.detach().to(dtype)
         self.fc_b = model.fc.bias.detach().to(dtype)
+        self.stem_s2d = None
+
+    def enable_s2d_stem(self):
+        """Re-express the 7x7 / stride-2 / pad-3 stem on 3 channels as a 4x4 / stride-1 / pad-0 convolution on the 2x2
+        space-to-depth image (12 -> 16 channels, 2 blocks of zero padding before and 1 after): the same sums, but a shape
+        cuDNN has tensor-core kernels for (the 3-channel conv ran on a legacy mma.sync kernel: half of the classifier's
+        time).  W'[o, (dy*2+dx)*3+c, a, b] = W[o, c, 2a+dy-1, 2b+dx-1] (zero where the index leaves 0..6).  The input
+        comes from ``space_to_depth_input`` (any tensor) or straight from the native preprocessing kernel."""
+        w, b, s, p = self.stem
+        if tuple(w.shape[1:]) != (3, 7, 7) or s != (2, 2) or p != (3, 3):
+            raise TypeError("s2d stem: expected a 3->C 7x7 stride-2 pad-3 convolution")
+        self.stem_s2d = (stem_weight_to_s2d(w.float()).to(self.dtype).contiguous(memory_format=torch.channels_last), b)
+        return self
+
+    def __call__(self, x: torch.Tensor, s2d_input: bool = False) -> torch.Tensor:
+        if self.stem_s2d is not None:
+            if not s2d_input:
+                x = space_to_depth_input(x)
+            x = torch.cudnn_convolution_relu(x, self.stem_s2d[0], self.stem_s2d[1], (1, 1), (0, 0), (1, 1), 1)
+        else:
+            w, b, s, p = self.stem
+            x = torch.cudnn_convolution_relu(x, w, b, s, p, (1, 1), 1)
+        return self._trunk(x)
 
     def _fold(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
         w = conv.weight.detach().float()
@@ -149,9 +182,7 @@ class FusedResNetInference:
         w = (w * scale[:, None, None, None]).to(self.dtype).contiguous(memory_format=torch.channels_last)
         return w, b.to(self.dtype), tuple(conv.stride), tuple(conv.padding)
 
-    def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        w, b, s, p = self.stem
-        x = torch.cudnn_convolution_relu(x, w, b, s, p, (1, 1), 1)
+    def _trunk(self, x: torch.Tensor) -> torch.Tensor:
         x = F.max_pool2d(x, 3, 2, 1)
         for (w1, b1, s1, p1), (w2, b2, s2, p2), ds in self.blocks:
             identity = x if ds is None else F.conv2d(x, ds[0], ds[1], ds[2], ds[3])
@@ -159,6 +190,33 @@ class FusedResNetInference:
             x = torch.cudnn_convolution_add_relu(out, w2, identity, 1.0, b2, s2, p2, (1, 1), 1)
         x = x.mean((2, 3))
         return F.linear(x, self.fc_w, self.fc_b)
+
+
+def stem_weight_to_s2d(w: torch.Tensor) -> torch.Tensor:
+    """[O,3,7,7] stride-2 pad-3 stem weights -> [O,16,4,4] stride-1 pad-0 weights on the space-to-depth input."""
+    o = w.shape[0]
+    w2 = torch.zeros(o, 16, 4, 4, dtype=w.dtype, device=w.device)
+    for dy in range(2):
+        for dx in range(2):
+            for a in range(4):
+                ky = 2 * a + dy - 1
+                if not 0 <= ky <= 6:
+                    continue
+                for b in range(4):
+                    kx = 2 * b + dx - 1
+                    if 0 <= kx <= 6:
+                        ch = (dy * 2 + dx) * 3
+                        w2[:, ch:ch + 3, a, b] = w[:, :, ky, kx]
+    return w2
+
+
+def space_to_depth_input(x: torch.Tensor) -> torch.Tensor:
+    """[B,3,H,W] (H, W even) -> [B,16,H/2+3,W/2+3]: out[b,(dy*2+dx)*3+c,Y,X] = x[b,c,2(Y-2)+dy,2(X-2)+dx], zero padded."""
+    b, c, h, w = x.shape
+    blocks = x.reshape(b, c, h // 2, 2, w // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(b, 4 * c, h // 2, w // 2)
+    out = x.new_zeros((b, 16, h // 2 + 3, w // 2 + 3))
+    out[:, :4 * c, 2:2 + h // 2, 2:2 + w // 2] = blocks
+    return out.contiguous(memory_format=torch.channels_last)
 
 
 class ResNet(_Wrapper):

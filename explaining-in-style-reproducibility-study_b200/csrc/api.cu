@@ -196,6 +196,21 @@ int sx_resize_aa_normalize(const float* in, void* out, int out_bf16, int B, int 
   return launch_resize_aa_normalize<float>(in, reinterpret_cast<float*>(out), B, IH, IW, OH, OW, nm, S(stream));
 }
 
+int sx_resize_aa_normalize_s2d(const float* in, void* out, int out_bf16, int B, int IH, int IW, int OH, int OW, int normalize,
+                               const float* mean3, const float* std3, sx_stream_t stream) {
+  SX_REQUIRE(in && out, "null argument");
+  SX_REQUIRE(B >= 0 && IH >= 1 && IW >= 1 && OH >= 2 && OW >= 2, "bad shape");
+  SX_REQUIRE(!normalize || (mean3 && std3), "normalize needs mean and std");
+  Norm3 nm{};
+  nm.on = normalize ? 1 : 0;
+  for (int c = 0; c < 3; ++c) {
+    nm.mean[c] = normalize ? mean3[c] : 0.f;
+    nm.std[c] = normalize ? std3[c] : 1.f;
+  }
+  if (out_bf16) return launch_resize_aa_normalize_s2d<__nv_bfloat16>(in, reinterpret_cast<__nv_bfloat16*>(out), B, IH, IW, OH, OW, nm, S(stream));
+  return launch_resize_aa_normalize_s2d<float>(in, reinterpret_cast<float*>(out), B, IH, IW, OH, OW, nm, S(stream));
+}
+
 // -------------------------------------------------------------------------------------------------
 // generator plan
 // -------------------------------------------------------------------------------------------------

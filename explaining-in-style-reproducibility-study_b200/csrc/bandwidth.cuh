@@ -345,7 +345,27 @@ int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const fl
 // (9 loads + 9 FMAs per channel); pixels whose neighbourhood touches the border (index clamping of the upsample,
 // reflect padding of the blur) take the generic two-step evaluation.
 // One thread = one 2x2 output quad (all 3 channels): the four pixels share the low-res neighbourhood, so 27 loads
-// serve 12 outputs (the one-pixel-per-thread version issued 27 per 3 and was LSU-bound at 22 ms per sweep step).
+// serve 12 outputs.  Border quads use the same 3x3 evaluation with the composite weights of their row / column
+// computed on the fly (blur taps reflected, bilinear sources clamped) -- the first versions sent them through the
+// generic 36-sample path, and with one border lane in half of the warps that path was 90 % of the kernel's time.
+__device__ __forceinline__ void blur_up_weights(int o, int n_in, float* wgt /*[3]: low-res o/2-1, o/2, o/2+1*/) {
+  const int base = (o >> 1) - 1;
+  wgt[0] = wgt[1] = wgt[2] = 0.f;
+#pragma unroll
+  for (int t = -1; t <= 1; ++t) {
+    const int u = reflect1(o + t, 2 * n_in);
+    int i0, i1;
+    float l0, l1;
+    bilinear_src(u, n_in, i0, i1, l0, l1);
+    const float kb = t == 0 ? 0.5f : 0.25f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (i0 - base == k) wgt[k] += kb * l0;
+      if (i1 - base == k) wgt[k] += kb * l1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) rgb_prev_up_blur_kernel(const float* __restrict__ prev, long long prev_bstride,
                                                                float* __restrict__ rgb, int h, int w) {
   const int H = 2 * h, W = 2 * w;
@@ -353,32 +373,36 @@ __global__ void __launch_bounds__(128) rgb_prev_up_blur_kernel(const float* __re
   const int i = blockIdx.y;
   const float* pp = prev + (long long)b * prev_bstride;
   float* dst = rgb + (long long)b * 3 * H * W;
-  const bool yint = i >= 1 && i <= h - 2;
+  float cye[3] = {0.3125f, 0.625f, 0.0625f}, cyo[3] = {0.0625f, 0.625f, 0.3125f};   // rows 2i / 2i+1 over low-res rows i-1, i, i+1
+  if (i < 1 || i > h - 2) {
+    blur_up_weights(2 * i, h, cye);
+    blur_up_weights(2 * i + 1, h, cyo);
+  }
+  const int r0 = max(i - 1, 0), r2 = min(i + 1, h - 1);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < w; j += gridDim.x * blockDim.x) {
-    if (yint && j >= 1 && j <= w - 2) {
+    float cxe[3] = {0.3125f, 0.625f, 0.0625f}, cxo[3] = {0.0625f, 0.625f, 0.3125f};
+    if (j < 1 || j > w - 2) {
+      blur_up_weights(2 * j, w, cxe);
+      blur_up_weights(2 * j + 1, w, cxo);
+    }
+    const int c0 = max(j - 1, 0), c2 = min(j + 1, w - 1);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* p = pp + (size_t)c * h * w + (size_t)(i - 1) * w + (j - 1);
-        float re[3], ro[3];   // even / odd output column of the three low-res rows
+    for (int c = 0; c < 3; ++c) {
+      const float* p = pp + (size_t)c * h * w;
+      const int rows[3] = {r0, i, r2};
+      float re[3], ro[3];   // even / odd output column of the three low-res rows
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float p0 = __ldg(p + r * w), p1 = __ldg(p + r * w + 1), p2 = __ldg(p + r * w + 2);
-          re[r] = 0.3125f * p0 + 0.625f * p1 + 0.0625f * p2;
-          ro[r] = 0.0625f * p0 + 0.625f * p1 + 0.3125f * p2;
-        }
-        float* d = dst + ((size_t)c * H + 2 * i) * W + 2 * j;
-        *reinterpret_cast<float2*>(d) = make_float2(0.3125f * re[0] + 0.625f * re[1] + 0.0625f * re[2],
-                                                    0.3125f * ro[0] + 0.625f * ro[1] + 0.0625f * ro[2]);
-        *reinterpret_cast<float2*>(d + W) = make_float2(0.0625f * re[0] + 0.625f * re[1] + 0.3125f * re[2],
-                                                        0.0625f * ro[0] + 0.625f * ro[1] + 0.3125f * ro[2]);
+      for (int r = 0; r < 3; ++r) {
+        const float* q = p + (size_t)rows[r] * w;
+        const float p0 = __ldg(q + c0), p1 = __ldg(q + j), p2 = __ldg(q + c2);
+        re[r] = cxe[0] * p0 + cxe[1] * p1 + cxe[2] * p2;
+        ro[r] = cxo[0] * p0 + cxo[1] * p1 + cxo[2] * p2;
       }
-    } else {
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        const int y = 2 * i + (q >> 1), x = 2 * j + (q & 1);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) dst[((size_t)c * H + y) * W + x] = up2_blur(pp + (size_t)c * h * w, nullptr, h, w, y, x);
-      }
+      float* d = dst + ((size_t)c * H + 2 * i) * W + 2 * j;
+      *reinterpret_cast<float2*>(d) = make_float2(cye[0] * re[0] + cye[1] * re[1] + cye[2] * re[2],
+                                                  cye[0] * ro[0] + cye[1] * ro[1] + cye[2] * ro[2]);
+      *reinterpret_cast<float2*>(d + W) = make_float2(cyo[0] * re[0] + cyo[1] * re[1] + cyo[2] * re[2],
+                                                      cyo[0] * ro[0] + cyo[1] * ro[1] + cyo[2] * ro[2]);
     }
   }
 }

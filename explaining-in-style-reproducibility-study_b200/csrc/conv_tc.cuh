@@ -101,6 +101,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One elected lane of a fully converged warp.  The TMA / MMA warps run their loops warp-uniformly and predicate only
+// the issuing instruction with this: inside an `if (lane == 0)` region the compiler cannot prove that the descriptor
+// operands of UTCHMMA / UBLKCP are warp-uniform and wraps every one of them in a waterfall loop
+// (ELECT ... BRA.U.ANY, ~47 SASS instructions per filter tap: the single issuing thread then paces the narrow layers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of BLOCK_K bf16
 // (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row groups SBO bytes apart, version 1 (Blackwell).
@@ -157,6 +170,79 @@ __device__ __forceinline__ void rgb_chunk32(const float* __restrict__ fr, const 
       a = fmaf(fr[j + 3], w4.w, a);
     }
     acc[c] = a;
+  }
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 issue two fp32 lanes per instruction) ----------------------------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// The generator's epilogue (leaky-ReLU on, bf16 NHWC output) on 32 accumulator columns, two columns per instruction:
+//   t = acc * d + (nz * nw + nb);  t = max(t, 0.2 t);  raw = bf16(t);  out = bf16(raw * m);  rgb_c += raw * rw_c
+// Same values as epi_chunk32 (the fused multiply-adds are the ones the compiler formed there; max(t, 0.2t) == lrelu);
+// the ToRGB partial sums run in two lanes (even / odd columns) that the caller adds at the end.
+// om / orw: 16 packed bf16x2 words each (modulated output, raw output).
+template <bool RGB>
+__device__ __forceinline__ void epi_fast32(const uint32_t* __restrict__ v, const float* __restrict__ dd, const float* __restrict__ nw,
+                                           const float* __restrict__ nb, const float* __restrict__ mm, float nz,
+                                           uint32_t* __restrict__ om, uint32_t* __restrict__ orw, const float* __restrict__ rw,
+                                           int rw_stride, uint64_t* __restrict__ racc) {
+  const uint64_t nz2 = pk2(nz, nz), c02 = pk2(0.2f, 0.2f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dd + j);
+    const float4 w4 = *reinterpret_cast<const float4*>(nw + j);
+    const float4 b4 = *reinterpret_cast<const float4*>(nb + j);
+    const float4 m4 = *reinterpret_cast<const float4*>(mm + j);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    if (RGB) {
+      r0 = *reinterpret_cast<const float4*>(rw + j);
+      r1 = *reinterpret_cast<const float4*>(rw + rw_stride + j);
+      r2 = *reinterpret_cast<const float4*>(rw + 2 * rw_stride + j);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = j + 2 * h;
+      const uint64_t d2 = h ? pk2(d4.z, d4.w) : pk2(d4.x, d4.y);
+      const uint64_t w2 = h ? pk2(w4.z, w4.w) : pk2(w4.x, w4.y);
+      const uint64_t b2 = h ? pk2(b4.z, b4.w) : pk2(b4.x, b4.y);
+      const uint64_t m2 = h ? pk2(m4.z, m4.w) : pk2(m4.x, m4.y);
+      const uint64_t t2 = fma2(pk2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), d2, fma2(nz2, w2, b2));
+      const uint64_t l2 = mul2(t2, c02);
+      float t0, t1, l0, l1;
+      upk2(t2, t0, t1);
+      upk2(l2, l0, l1);
+      const uint32_t raw = bf16x2_rn(fmaxf(t0, l0), fmaxf(t1, l1));
+      orw[c >> 1] = raw;
+      const uint64_t fr2 = pk2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+      float f0, f1;
+      upk2(mul2(fr2, m2), f0, f1);
+      om[c >> 1] = bf16x2_rn(f0, f1);
+      if (RGB) {
+        racc[0] = fma2(fr2, h ? pk2(r0.z, r0.w) : pk2(r0.x, r0.y), racc[0]);
+        racc[1] = fma2(fr2, h ? pk2(r1.z, r1.w) : pk2(r1.x, r1.y), racc[1]);
+        racc[2] = fma2(fr2, h ? pk2(r2.z, r2.w) : pk2(r2.x, r2.y), racc[2]);
+      }
+    }
   }
 }
 
@@ -233,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 
   if (warp_id == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -241,16 +327,18 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         const int c0 = (kb - tap * kc_per_tap) * BLOCK_K;
         const int dy = tap / p.KS - pad, dx = tap % p.KS - pad;
         mbar_wait(&empty_bar[stage], phase ^ 1, 0);
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0, x0 + dx, y0 + dy, b0);
-        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], tap * p.Ci + c0, n0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0, x0 + dx, y0 + dy, b0);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], tap * p.Ci + c0, n0);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp_id == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -259,17 +347,20 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
         tc_fence_after();
         const uint64_t da = make_smem_desc<BLOCK_K>(smem_u32(smem_a + stage * Cfg::kABytes));
         const uint64_t db = make_smem_desc<BLOCK_K>(smem_u32(smem_b + stage * Cfg::kBBytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance the start address by k * 16 bf16 = 32 bytes inside the swizzled row (>>4 -> +2)
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance the start address by k * 16 bf16 = 32 bytes inside the swizzled row (>>4 -> +2)
+            umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
+      if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const ConvEpilogue& ep = p.ep;

@@ -108,6 +108,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BLOCK_N;
+  // Each CTA walks a CONTIGUOUS range of tiles (sample-major, then rows, then columns): the tile's sample -- and with it
+  // the per-sample epilogue tables -- changes once per several hundred tiles instead of every other tile, and
+  // consecutive tiles share halo columns in L2.
+  const int tile_begin = (int)((long long)blockIdx.x * p.num_tiles / gridDim.x);
+  const int tile_end = (int)((long long)(blockIdx.x + 1) * p.num_tiles / gridDim.x);
 #ifdef SX_HALO_DEBUG_KNOBS   // bottleneck experiments only (profiles/README.md); never in the shipped library
   const int dbg = p.debug;
 #else
@@ -131,18 +136,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp_id == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    {
       if (RESIDENT_B) {
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(p.num_b_tiles * Cfg::kBBytes));
-        for (int i = 0; i < p.num_b_tiles; ++i) {
-          const int chunk = i / 9, tap = i - chunk * 9;
-          tma_load_2d(smem_b + (size_t)i * Cfg::kBBytes, &tmap_b, &b_full[0], tap * p.Ci + chunk * BLOCK_K, n0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[0], (uint32_t)(p.num_b_tiles * Cfg::kBBytes));
+          for (int i = 0; i < p.num_b_tiles; ++i) {
+            const int chunk = i / 9, tap = i - chunk * 9;
+            tma_load_2d(smem_b + (size_t)i * Cfg::kBBytes, &tmap_b, &b_full[0], tap * p.Ci + chunk * BLOCK_K, n0);
+          }
         }
+        __syncwarp();
       }
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int b = tile >> p.tpb_shift;
         const int tr = tile - (b << p.tpb_shift);
         const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
@@ -152,34 +160,43 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // low-resolution source box of the halo box: rows y0/2-1 .. y0/2+8, columns x0/2-1 .. x0/2+4 (zero-filled
             // outside the image; the producers clamp instead, like torch's bilinear kernel)
             mbar_wait(&s_empty[as], aph ^ 1, 10);
-            mbar_arrive_expect_tx(&s_full[as], Cfg::kSrcBytes);
-            tma_load_4d(smem_src + as * Cfg::kSrcBytes, &tmap_a, &s_full[as], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&s_full[as], Cfg::kSrcBytes);
+              tma_load_4d(smem_src + as * Cfg::kSrcBytes, &tmap_a, &s_full[as], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
+            }
+            __syncwarp();
             if (++as == UPS_S_STAGES) { as = 0; aph ^= 1; }
           } else {
             mbar_wait(&a_empty[as], aph ^ 1, 10);
-            if (dbg & 4) {
-              mbar_arrive(&a_full[as]);
-            } else {
-              mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
-              tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+            if (elect_one()) {
+              if (dbg & 4) {
+                mbar_arrive(&a_full[as]);
+              } else {
+                mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
+                tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+              }
             }
+            __syncwarp();
             if (++as == A_STAGES) { as = 0; aph ^= 1; }
           }
           if (!RESIDENT_B) {
+#pragma unroll 1
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[bs], bph ^ 1, 11);
-              mbar_arrive_expect_tx(&b_full[bs], Cfg::kBBytes);
-              tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmap_b, &b_full[bs], tap * p.Ci + chunk * BLOCK_K, n0);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&b_full[bs], Cfg::kBBytes);
+                tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmap_b, &b_full[bs], tap * p.Ci + chunk * BLOCK_K, n0);
+              }
+              __syncwarp();
               if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
             }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp_id == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       constexpr uint32_t sbo = HALO_W * Cfg::kRowBytes;
       if (RESIDENT_B) {
@@ -188,46 +205,63 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const uint32_t a_base0 = smem_u32(smem_a), b_base0 = smem_u32(smem_b);
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int chunk = 0; chunk < p.kchunks; ++chunk) {
           mbar_wait(&a_full[as], aph, 14);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + as * Cfg::kABytes);
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t b_addr;
-            if (RESIDENT_B) {
-              b_addr = smem_u32(smem_b + (size_t)(chunk * 9 + tap) * Cfg::kBBytes);
-            } else {
+          // descriptors of tap 0; every other tap / k step is this plus a compile-time constant (fully unrolled)
+          const uint64_t da0 = make_smem_desc_sbo<BLOCK_K>(a_base0 + (uint32_t)(as * Cfg::kABytes), sbo);
+          const uint64_t db_res = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(chunk * 9 * Cfg::kBBytes));
+          if (RESIDENT_B) {
+            // weights resident: nothing to wait for inside the chunk -- one election, 9 x BLOCK_K/16 back-to-back MMAs
+            if (elect_one()) {
+              if (!(dbg & 2)) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                  const int ky = tap / 3, kx = tap - ky * 3;
+                  const uint64_t da = da0 + (uint64_t)(((ky * HALO_W + kx) * Cfg::kRowBytes) >> 4);
+                  const uint64_t db = db_res + (uint64_t)((tap * Cfg::kBBytes) >> 4);
+#pragma unroll
+                  for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                    umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_full[bs], bph, 15);
               tc_fence_after();
-              b_addr = smem_u32(smem_b + bs * Cfg::kBBytes);
-            }
-            const int ky = tap / 3, kx = tap - ky * 3;
-            const uint64_t da = make_smem_desc_sbo<BLOCK_K>(a_base + (uint32_t)((ky * HALO_W + kx) * Cfg::kRowBytes), sbo);
-            const uint64_t db = make_smem_desc<BLOCK_K>(b_addr);
-            if (!(dbg & 2)) {
+              const uint64_t db = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(bs * Cfg::kBBytes));
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const uint64_t da = da0 + (uint64_t)(((ky * HALO_W + kx) * Cfg::kRowBytes) >> 4);
+              if (elect_one()) {
+                if (!(dbg & 2)) {
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
-            }
-            if (!RESIDENT_B) {
-              umma_commit(&b_empty[bs]);
+                  for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                    umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&b_empty[bs]);
+              }
+              __syncwarp();
               if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
             }
           }
-          umma_commit(&a_empty[as]);
+          if (elect_one()) umma_commit(&a_empty[as]);
+          __syncwarp();
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) accph ^= 1;
       }
     }
-    __syncwarp();
   } else if (UPS && warp_id >= 6) {
     // ===================== fused bilinear 2x upsample: A-operand producers (warps 6..9) =====================
     // out halo pixel (hy, hx) <-> image pixel (y0-1+hy, x0-1+hx); y0, x0 are even, so halo rows (2k, 2k+1) interpolate
@@ -242,7 +276,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int seg = unit / 5;                   // halo rows 6seg .. 6seg+5 <- source rows 3seg .. 3seg+3
     int as = 0, ss = 0;
     uint32_t aph = 0, sph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int b = tile >> p.tpb_shift;
       const int tr = tile - (b << p.tpb_shift);
       const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
@@ -322,9 +356,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int yy = r >> 3, xx = r & 7;
     int acc = 0;
     uint32_t accph = 0;
-    // Per-tile operands of the epilogue (demod / next-style rows of the tile's sample, the pixel's noise value) are
-    // PREFETCHED one tile ahead into registers and published to the other table slot after the current tile is done:
-    // their global-load latency used to be exposed once per tile (31 % of all stall samples in ncu).
     auto tile_coords = [&](int tile, int& b, int& x, int& y) {
       b = tile >> p.tpb_shift;
       const int tr = tile - (b << p.tpb_shift);
@@ -337,13 +368,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int S = ep.noise_size;
       return __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
     };
-    constexpr int TPT = (BLOCK_N + 127) / 128;   // table entries per epilogue thread
-    constexpr int TPT3 = (3 * BLOCK_N + 127) / 128;
     constexpr bool fuse_rgb = FUSE_RGB;   // compile-time: the plain instantiation carries none of the ToRGB registers
     const long long HWl = (long long)p.H * p.W;
-    // raw prefetched values only: NO arithmetic on them before the tile has been processed, otherwise the load latency
-    // lands on the per-tile critical path again (ncu: long_scoreboard on the `+ 1` of the style rows)
-    float d_nx[TPT], m_nx[TPT], ws_nx[TPT3], ww_nx[TPT3];
     auto load_rgb_prev = [&](int b, int x, int y, float* v) {
       v[0] = v[1] = v[2] = 0.f;
       if (fuse_rgb && ep.rgb_accumulate) {
@@ -352,95 +378,116 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int c = 0; c < 3; ++c) v[c] = __ldg(src + c * HWl);
       }
     };
-    auto load_tables = [&](int b) {
+    // per-sample tables (demod coefficients, next-layer style + 1, fused-ToRGB weights) live in two shared-memory slots;
+    // a sample change (rare: tiles are walked sample-major) fills the other slot and synchronises the four warps once
+    auto write_tables = [&](int slot, int b) {
+      for (int i = et; i < BLOCK_N; i += 128) {
+        s_d[slot * BLOCK_N + i] = ep.dcoef ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + i) : 1.f;
+        s_m[slot * BLOCK_N + i] = ep.next_style ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) + 1.f : 1.f;
+      }
       if (fuse_rgb) {
-#pragma unroll
-        for (int k = 0; k < TPT3; ++k) {
-          const int i = et + k * 128;
+        for (int i = et; i < 3 * BLOCK_N; i += 128) {
           const int o = i % BLOCK_N;
-          const bool in = i < 3 * BLOCK_N;
-          ws_nx[k] = in ? __ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) : 0.f;
-          ww_nx[k] = in ? __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < TPT; ++k) {
-        const int i = et + k * 128;
-        d_nx[k] = (i < BLOCK_N && ep.dcoef) ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + i) : 1.f;
-        m_nx[k] = (i < BLOCK_N && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) : 0.f;
-      }
-    };
-    auto store_tables = [&](int slot) {
-#pragma unroll
-      for (int k = 0; k < TPT; ++k) {
-        const int i = et + k * 128;
-        if (i < BLOCK_N) { s_d[slot * BLOCK_N + i] = d_nx[k]; s_m[slot * BLOCK_N + i] = m_nx[k] + 1.f; }
-      }
-      if (fuse_rgb) {
-#pragma unroll
-        for (int k = 0; k < TPT3; ++k) {
-          const int i = et + k * 128;
-          if (i < 3 * BLOCK_N) s_rgbw[slot * 3 * BLOCK_N + i] = (ws_nx[k] + 1.f) * ww_nx[k];
+          s_rgbw[slot * 3 * BLOCK_N + i] =
+              (__ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o);
         }
       }
     };
-    int b = 0, x = 0, y = 0;
+    // the generator's configuration (activation on, bf16 NHWC or no feature-map output) takes the packed fast path
+    const bool fast = ep.act != 0 && !ep.out_nchw_f32;
+    int b = 0, x = 0, y = 0, cur_b = -1, slot = 1;
     float nz = 0.f, rgbp[3] = {0.f, 0.f, 0.f};
-    if ((int)blockIdx.x < p.num_tiles) {
-      tile_coords(blockIdx.x, b, x, y);
+    if (tile_begin < tile_end) {
+      tile_coords(tile_begin, b, x, y);
       nz = load_noise(b, x, y);
       load_rgb_prev(b, x, y, rgbp);
-      load_tables(b);
-      store_tables(0);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const float* dd = s_d + acc * BLOCK_N;
-      const float* mm = s_m + acc * BLOCK_N;
-      const float* rw = s_rgbw + acc * 3 * BLOCK_N;
-      float rgb_acc[3] = {rgbp[0], rgbp[1], rgbp[2]};
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      if (b != cur_b) {
+        slot ^= 1;
+        write_tables(slot, b);
+        cur_b = b;
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // tables (and, the first time, s_nw / s_nb) visible to all four warps
+      }
+      const float* dd = s_d + slot * BLOCK_N;
+      const float* mm = s_m + slot * BLOCK_N;
+      const float* rw = s_rgbw + slot * 3 * BLOCK_N;
       const long long pix = ((long long)b * p.H + y) * p.W + x;
-      // prefetch the next tile's operands (consumed after this tile's TMEM drain)
-      const int next = tile + gridDim.x;
-      int b2 = 0, x2 = 0, y2 = 0;
+      // prefetch the next tile's per-pixel operands (consumed after this tile's TMEM drain)
+      int b2 = b, x2 = 0, y2 = 0;
       float nz2 = 0.f, rgbp2[3] = {0.f, 0.f, 0.f};
-      if (next < p.num_tiles) {
-        tile_coords(next, b2, x2, y2);
+      if (tile + 1 < tile_end) {
+        tile_coords(tile + 1, b2, x2, y2);
         nz2 = load_noise(b2, x2, y2);
         load_rgb_prev(b2, x2, y2, rgbp2);
-        load_tables(b2);
       }
       mbar_wait(&tmem_full[acc], accph, 16);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < ((dbg & 1) ? 0 : BLOCK_N); c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-        tmem_ld_wait();
-        float f[32], fr[32];
-        epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
-        if (fuse_rgb) rgb_chunk32(fr, rw + c0, BLOCK_N, rgb_acc);
-        if (!ep.out) {
-        } else if (ep.out_nchw_f32) {
-          float* out = reinterpret_cast<float*>(ep.out);
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      float rgb_acc[3] = {rgbp[0], rgbp[1], rgbp[2]};
+      if (dbg & 1) {
+      } else if (fast) {
+        constexpr int NCH = BLOCK_N / 32;
+        uint32_t v[NCH > 1 ? 2 : 1][32];
+        uint64_t racc[3] = {pk2(rgbp[0], 0.f), pk2(rgbp[1], 0.f), pk2(rgbp[2], 0.f)};
+        tmem_ld32(tbase, v[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
-        } else {
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int c0 = ch * 32;
+          tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld32(tbase + (uint32_t)(c0 + 32), v[(ch + 1) & 1]);   // next chunk in flight during the math
+          uint32_t om[16], orw[16];
+          epi_fast32<fuse_rgb>(v[ch & 1], dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, om, orw, rw + c0, BLOCK_N, racc);
+          if (ep.out) {
+            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            pack(f + j, pk);
-            *reinterpret_cast<uint4*>(out + j) = pk;
+            for (int k = 0; k < 4; ++k) out[k] = make_uint4(om[4 * k], om[4 * k + 1], om[4 * k + 2], om[4 * k + 3]);
+          }
+          if (ep.out_raw) {
+            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] = make_uint4(orw[4 * k], orw[4 * k + 1], orw[4 * k + 2], orw[4 * k + 3]);
           }
         }
-        if (ep.out_raw) {
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+        if (fuse_rgb) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            pack(fr + j, pk);
-            *reinterpret_cast<uint4*>(out + j) = pk;
+          for (int c = 0; c < 3; ++c) {
+            float lo, hi;
+            upk2(racc[c], lo, hi);
+            rgb_acc[c] = lo + hi;
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float f[32], fr[32];
+          epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
+          if (fuse_rgb) rgb_chunk32(fr, rw + c0, BLOCK_N, rgb_acc);
+          if (!ep.out) {
+          } else if (ep.out_nchw_f32) {
+            float* out = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
+          } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pack(f + j, pk);
+              *reinterpret_cast<uint4*>(out + j) = pk;
+            }
+          }
+          if (ep.out_raw) {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pack(fr + j, pk);
+              *reinterpret_cast<uint4*>(out + j) = pk;
+            }
           }
         }
       }
@@ -453,10 +500,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1;
-      if (next < p.num_tiles) store_tables(acc);
       b = b2; x = x2; y = y2; nz = nz2;
       rgbp[0] = rgbp2[0]; rgbp[1] = rgbp2[1]; rgbp[2] = rgbp2[2];
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // next tile's tables visible; everyone is done with the old slot
     }
   }
 

@@ -80,6 +80,87 @@ __global__ void __launch_bounds__(256) resize_aa_normalize_kernel(const float* _
   }
 }
 
+// Space-to-depth variant for the ResNet stem: the 7x7 / stride-2 / pad-3 convolution on 3 channels (which cuDNN runs on
+// a legacy mma.sync kernel at ~17 TFLOP/s) equals a 4x4 / stride-1 / pad-0 convolution on the 2x2 space-to-depth image
+// with 12 (padded to 16) channels, padded by 2 blocks before and 1 block after (classifiers.py: stem_s2d weights).
+//   out[b, Y, X, (dy*2+dx)*3 + c] = resized[b, c, 2(Y-2)+dy, 2(X-2)+dx]   (0 outside the image; channels 12..15 = 0)
+// out is the memory of a channels_last [B, 16, OH/2+3, OW/2+3] tensor.  One thread = one (Y, X) block = 32 B of bf16.
+template <typename T, int TAPS>
+__global__ void __launch_bounds__(128) resize_aa_normalize_s2d_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int IH,
+                                                                      int IW, int OH, int OW, Norm3 nm) {
+  const float sy = (float)IH / (float)OH, sx_ = (float)IW / (float)OW;
+  const float sup_y = sy >= 1.f ? sy : 1.f, sup_x = sx_ >= 1.f ? sx_ : 1.f;
+  const float inv_y = sy >= 1.f ? 1.f / sy : 1.f, inv_x = sx_ >= 1.f ? 1.f / sx_ : 1.f;
+  const int PH = OH / 2 + 3, PW = OW / 2 + 3;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= PW) return;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.f;
+  const int by = Y - 2, bx = X - 2;
+  if (by >= 0 && by < OH / 2 && bx >= 0 && bx < OW / 2) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      float wy[TAPS];
+      int ymin, ysize;
+      aa_weights<TAPS>(2 * by + dy, sy, sup_y, inv_y, IH, ymin, ysize, wy);
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float wx[TAPS];
+        int xmin, xsize;
+        aa_weights<TAPS>(2 * bx + dx, sx_, sup_x, inv_x, IW, xmin, xsize, wx);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* plane = in + ((size_t)b * 3 + c) * IH * IW;
+          float acc = 0.f;
+#pragma unroll
+          for (int y = 0; y < TAPS; ++y) {
+            if (y < ysize) {
+              const float* row = plane + (size_t)(ymin + y) * IW + xmin;
+              float t = __ldg(row) * wx[0];
+#pragma unroll
+              for (int x = 1; x < TAPS; ++x)
+                if (x < xsize) t += __ldg(row + x) * wx[x];
+              acc = y == 0 ? t * wy[0] : acc + t * wy[y];
+            }
+          }
+          if (nm.on) acc = (acc - nm.mean[c]) / nm.std[c];
+          v[(dy * 2 + dx) * 3 + c] = to_f(from_f<T>(acc));
+        }
+      }
+    }
+  }
+  constexpr int V = Elem<T>::kVec;
+  using vec_t = typename Elem<T>::vec_t;
+  vec_t* dst = reinterpret_cast<vec_t*>(out + (((size_t)b * PH + Y) * PW + X) * 16);
+#pragma unroll
+  for (int k = 0; k < 16 / V; ++k) {
+    vec_t pk;
+    pack(v + k * V, pk);
+    dst[k] = pk;
+  }
+}
+
+template <typename T>
+int launch_resize_aa_normalize_s2d(const float* in, T* out, int B, int IH, int IW, int OH, int OW, const Norm3& nm, cudaStream_t st) {
+  if (B == 0) return SX_OK;
+  SX_REQUIRE(OH % 2 == 0 && OW % 2 == 0, "resize(s2d): output size %dx%d must be even", OH, OW);
+  const float sy = (float)IH / OH, sxx = (float)IW / OW;
+  const float sup = fmaxf(sy >= 1.f ? sy : 1.f, sxx >= 1.f ? sxx : 1.f);
+  const int taps = (int)(2.f * sup) + 2;
+  SX_REQUIRE(taps <= AA_MAX_TAPS, "resize: scale factor %.2f too large (max %d taps)", sup, AA_MAX_TAPS);
+  const int PH = OH / 2 + 3, PW = OW / 2 + 3;
+  dim3 grid((PW + 127) / 128, PH, B);
+  SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "resize: grid too large");
+  if (taps <= 4)
+    resize_aa_normalize_s2d_kernel<T, 4><<<grid, 128, 0, st>>>(in, out, B, IH, IW, OH, OW, nm);
+  else
+    resize_aa_normalize_s2d_kernel<T, AA_MAX_TAPS><<<grid, 128, 0, st>>>(in, out, B, IH, IW, OH, OW, nm);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
 template <typename T>
 int launch_resize_aa_normalize(const float* in, T* out, int B, int IH, int IW, int OH, int OW, const Norm3& nm, cudaStream_t st) {
   if (B == 0) return SX_OK;

@@ -96,6 +96,13 @@ int sx_linear_fwd(const float* x, const float* weight, const float* bias, float*
 int sx_resize_aa_normalize(const float* in, void* out, int out_bf16, int B, int IH, int IW, int OH, int OW, int normalize,
                            const float* mean3, const float* std3, sx_stream_t stream);
 
+/* Same preprocessing, written as the 2x2 space-to-depth image the re-expressed ResNet stem consumes (the 7x7/stride-2/
+ * pad-3 convolution of torchvision's resnet conv1 == a 4x4/stride-1/pad-0 convolution on this tensor; classifiers.py):
+ * out[b, Y, X, (dy*2+dx)*3 + c] = preprocessed[b, c, 2(Y-2)+dy, 2(X-2)+dx], zero outside the image and in channels
+ * 12..15.  out: [B, OH/2+3, OW/2+3, 16] fp32 or bf16 = the memory of a channels_last [B,16,OH/2+3,OW/2+3] tensor. */
+int sx_resize_aa_normalize_s2d(const float* in, void* out, int out_bf16, int B, int IH, int IW, int OH, int OW, int normalize,
+                               const float* mean3, const float* std3, sx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Generator plan -- sits under Generator.forward (ST:794-825) and the notebook's repeated
  * stylex.G(w, noise) calls (NB:318,382).

@@ -444,6 +444,32 @@ def test_native_preprocess_matches_torchvision(dev, size):
         sx.make_classifier("mobilenet", model, size).use_native_preprocess(True)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
+def test_s2d_stem_matches_eager_and_native_s2d_preprocess_is_exact(dev, dtype, tol):
+    """the re-expressed ResNet stem (4x4 stride-1 conv on the space-to-depth image) is the same function, and the native
+    kernel that writes the space-to-depth network input equals space_to_depth(native preprocess) bit for bit."""
+    from stylex_b200.classifiers import space_to_depth_input
+    model = synthetic.make_classifier_model("resnet", 5)
+    g = torch.Generator().manual_seed(1)
+    imgs = (torch.rand(6, 3, 256, 256, generator=g) * 2 - 0.5)
+    clf = sx.make_classifier("resnet", model, 256)
+    synthetic.calibrate_classifier(model, clf.preprocess, imgs, chunk=6)
+    clf.to(dev).set_compute(dtype, channels_last=True)
+    x = imgs.to(dev)
+    ref = clf.classify_images(x)
+    clf.fuse_for_inference()
+    clf.fused.enable_s2d_stem()
+    got = clf.classify_images(x)                      # torch preprocessing + torch space-to-depth
+    assert float((got - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    plain = clf._native_pre(x)
+    s2d = clf._native_pre(x, s2d=True)
+    assert s2d.shape == (6, 16, 115, 115) and s2d.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(s2d, space_to_depth_input(plain))
+    clf.use_native_preprocess(True)
+    got2 = clf.classify_images(x)                     # native space-to-depth preprocessing
+    assert float((got2 - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
 def test_edge_cases_empty_and_ragged(dev):
     """empty batches are no-ops, a single latent works (min == max: every shift is 0), odd batch sizes and coordinate
     subsets that straddle conv boundaries are handled."""

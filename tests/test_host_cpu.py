@@ -165,3 +165,16 @@ def test_classifier_wrappers_match_reference_semantics():
     m = sx.MobileNet(model=net, image_size=64)
     assert torch.allclose(m.classify_images(x), net((x - mean) / std), atol=1e-6)
     assert r.resnet_dim == 224 and m.image_size == 64 and r.normalize
+
+
+def test_s2d_stem_weights_reproduce_the_7x7_stride2_conv():
+    """classifiers.stem_weight_to_s2d / space_to_depth_input: conv(x, W, stride 2, pad 3) == conv(s2d(x), W', stride 1, pad 0)."""
+    from stylex_b200.classifiers import space_to_depth_input, stem_weight_to_s2d
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(8, 3, 7, 7, generator=g)
+    for size in (32, 224):
+        x = torch.randn(2, 3, size, size, generator=g)
+        ref = torch.nn.functional.conv2d(x, w, None, 2, 3)
+        got = torch.nn.functional.conv2d(space_to_depth_input(x), stem_weight_to_s2d(w), None, 1, 0)
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) <= 1e-4
