@@ -53,6 +53,8 @@ def parse():
                     help="fused: BatchNorm folded + PyTorch's fused cuDNN conv+bias+ReLU ops; eager: the module as is")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "plain"],
                     help="fused classifier stem: the 7x7/stride-2 conv re-expressed as a 4x4/stride-1 conv on the space-to-depth input, or as is")
+    ap.add_argument("--maxpool", default="native", choices=["native", "torch"],
+                    help="fused classifier stem max-pool: sx_maxpool3x3s2_nhwc (bit-identical) or F.max_pool2d")
     ap.add_argument("--preprocess", default="native", choices=["native", "torch"],
                     help="classifier input pipeline: one native kernel or torchvision resize + Normalize")
     ap.add_argument("--latents-per-step", type=int, default=1)
@@ -250,12 +252,15 @@ def run_ours(args):
             clf.fuse_for_inference()
             if args.stem == "s2d":
                 clf.fused.enable_s2d_stem()
+            if args.maxpool == "native":
+                clf.fused.enable_native_pool()
             got = clf.classify_images(probe)
             torch.cuda.synchronize()
             tol = 0.05 * float(ref_logits.abs().max()) + 0.05
             if not torch.isfinite(got).all() or float((got - ref_logits).abs().max()) > tol:
                 raise RuntimeError(f"fused classifier deviates: {float((got - ref_logits).abs().max()):.3e} > {tol:.3e}")
-            clf_mode = "fused (BN folded, aten::cudnn_convolution_[add_]relu" + (", 7x7/2 stem as 4x4/1 on space-to-depth input)" if args.stem == "s2d" else ")")
+            clf_mode = ("fused (BN folded, aten::cudnn_convolution_[add_]relu" + (", 7x7/2 stem as 4x4/1 on space-to-depth input" if args.stem == "s2d" else "")
+                        + (", native 3x3/2 max-pool)" if args.maxpool == "native" else ")"))
         except Exception as e:  # noqa: BLE001 -- any failure means: keep the eager module, say so in the JSON
             clf.fused = None
             clf_mode = f"eager (fused path unavailable: {type(e).__name__}: {str(e)[:120]})"

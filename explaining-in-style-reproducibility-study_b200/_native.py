@@ -51,6 +51,7 @@ SIGNATURES = {
                                        POINTER(c_float), c_void_p]),
     "sx_resize_aa_normalize_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),
                                            POINTER(c_float), c_void_p]),
+    "sx_maxpool3x3s2_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sx_generator_create": (c_int, [POINTER(c_int), POINTER(c_int), c_int, c_int, POINTER(c_void_p)]),
     "sx_generator_destroy": (None, [c_void_p]),
     "sx_generator_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(sx_block_params), c_void_p]),

@@ -11,7 +11,10 @@ normalisation, raw logits out).  Differences, all forced by the environment:
   is not on the measured path.
 
 BASELINE north_star: "The classifier forward (ResNet-18/MobileNetV2) runs through PyTorch in
-the same stream" -- nothing here calls the native library.
+the same stream".  The convolutions / linear layers always do.  Two opt-in throughput switches replace the
+bandwidth-bound passes AROUND them with native kernels on that stream (`use_native_preprocess`: resize + normalise +
+cast + layout in one pass; `FusedResNetInference.native_pool`: the 3x3/2 stem max-pool, bit-identical to ATen's); both
+are off unless asked for and each is validated against the eager module by its caller (bench.py, tests).
 """
 from __future__ import annotations
 
@@ -145,11 +148,39 @@ class FusedResNetInference:
             for blk in layer:
                 if type(blk).__name__ != "BasicBlock":
                     raise TypeError("fuse_for_inference supports BasicBlock ResNets (resnet18/34)")
-                ds = None if blk.downsample is None else self._fold(blk.downsample[0], blk.downsample[1])
-                self.blocks.append((self._fold(blk.conv1, blk.bn1), self._fold(blk.conv2, blk.bn2), ds))
+                c1 = self._fold(blk.conv1, blk.bn1)
+                w2, b2, s2, p2 = self._fold(blk.conv2, blk.bn2, keep_fp32_bias=True)
+                ds = None
+                if blk.downsample is not None:
+                    # the shortcut conv's (folded-BN) bias joins conv2's bias: relu(conv2(.) + b2 + (ds(x) + bd)) -- one
+                    # elementwise pass over the shortcut less per downsampling block
+                    wd, bd, sd_, pd = self._fold(blk.downsample[0], blk.downsample[1], keep_fp32_bias=True)
+                    b2 = b2 + bd
+                    ds = (wd, None, sd_, pd)
+                self.blocks.append((c1, (w2, b2.to(dtype), s2, p2), ds))
         self.fc_w = model.fc.weight.detach().to(dtype)
         self.fc_b = model.fc.bias.detach().to(dtype)
         self.stem_s2d = None
+        self.native_pool = False
+
+    def enable_native_pool(self, on: bool = True):
+        """Opt-in: the 3x3 / stride-2 / pad-1 max-pool after the stem runs as sx_maxpool3x3s2_nhwc (bit-identical to
+        ``F.max_pool2d``; ATen's channels_last kernel reached ~0.7 TB/s on the [B,64,112,112] stem output)."""
+        self.native_pool = on
+        return self
+
+    def _pool(self, x: torch.Tensor) -> torch.Tensor:
+        if not (self.native_pool and x.is_cuda and x.dtype in (torch.bfloat16, torch.float32)
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            return F.max_pool2d(x, 3, 2, 1)
+        from . import _native as N
+
+        b, c, h, w = x.shape
+        out = torch.empty((b, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1), device=x.device, dtype=x.dtype,
+                          memory_format=torch.channels_last)
+        N.check(N.lib().sx_maxpool3x3s2_nhwc(x.data_ptr(), out.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0,
+                                             b, h, w, c, N.stream_ptr()), "sx_maxpool3x3s2_nhwc")
+        return out
 
     def enable_s2d_stem(self):
         """Re-express the 7x7 / stride-2 / pad-3 stem on 3 channels as a 4x4 / stride-1 / pad-0 convolution on the 2x2
@@ -173,17 +204,17 @@ class FusedResNetInference:
             x = torch.cudnn_convolution_relu(x, w, b, s, p, (1, 1), 1)
         return self._trunk(x)
 
-    def _fold(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    def _fold(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, keep_fp32_bias: bool = False):
         w = conv.weight.detach().float()
         scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
         b = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
         if conv.bias is not None:
             b = b + conv.bias.detach().float() * scale
         w = (w * scale[:, None, None, None]).to(self.dtype).contiguous(memory_format=torch.channels_last)
-        return w, b.to(self.dtype), tuple(conv.stride), tuple(conv.padding)
+        return w, (b if keep_fp32_bias else b.to(self.dtype)), tuple(conv.stride), tuple(conv.padding)
 
     def _trunk(self, x: torch.Tensor) -> torch.Tensor:
-        x = F.max_pool2d(x, 3, 2, 1)
+        x = self._pool(x)
         for (w1, b1, s1, p1), (w2, b2, s2, p2), ds in self.blocks:
             identity = x if ds is None else F.conv2d(x, ds[0], ds[1], ds[2], ds[3])
             out = torch.cudnn_convolution_relu(x, w1, b1, s1, p1, (1, 1), 1)

@@ -211,6 +211,14 @@ int sx_resize_aa_normalize_s2d(const float* in, void* out, int out_bf16, int B, 
   return launch_resize_aa_normalize_s2d<float>(in, reinterpret_cast<float*>(out), B, IH, IW, OH, OW, nm, S(stream));
 }
 
+int sx_maxpool3x3s2_nhwc(const void* in, void* out, int is_bf16, int B, int H, int W, int C, sx_stream_t stream) {
+  SX_REQUIRE(in && out, "null argument");
+  SX_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 1, "bad shape");
+  if (is_bf16)
+    return launch_maxpool3x3s2_nhwc<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, S(stream));
+  return launch_maxpool3x3s2_nhwc<float>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), B, H, W, C, S(stream));
+}
+
 // -------------------------------------------------------------------------------------------------
 // generator plan
 // -------------------------------------------------------------------------------------------------

@@ -142,6 +142,60 @@ __global__ void __launch_bounds__(128) resize_aa_normalize_s2d_kernel(const floa
   }
 }
 
+// ---- max_pool2d(kernel 3, stride 2, padding 1) on a channels_last bf16 / fp32 tensor (torchvision ResNet stem pool) -----------
+// ATen's max_pool_forward_nhwc ran at ~0.7 TB/s on the [B,64,112,112] stem output (9 % of the AttFind step).  One thread =
+// one output pixel x one 16-byte channel group: up to 9 vector loads (the 2.25x re-read is served by L1/L2), a packed max,
+// one vector store.  Padding never wins (-inf), NaNs propagate like torch's kernel; the result is bit-identical.
+__device__ __forceinline__ uint4 vmax(const uint4& a, const uint4& b, __nv_bfloat16) {
+  uint4 r;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __hmax2_nan(x[i], y[i]);
+  return r;
+}
+__device__ __forceinline__ float4 vmax(const float4& a, const float4& b, float) {
+  auto m = [](float p, float q) { return (p != p || q != q) ? __int_as_float(0x7fffffff) : fmaxf(p, q); };
+  return make_float4(m(a.x, b.x), m(a.y, b.y), m(a.z, b.z), m(a.w, b.w));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C,
+                                                                int OH, int OW) {
+  constexpr int V = Elem<T>::kVec;
+  using vec_t = typename Elem<T>::vec_t;
+  const unsigned groups = (unsigned)(C / V);
+  const unsigned total = (unsigned)B * OH * OW * groups;   // < 2^31 (checked by the launcher): 32-bit index arithmetic
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned g = i % groups;
+    unsigned t = i / groups;
+    const int ox = (int)(t % OW);
+    t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    const int y0 = max(2 * oy - 1, 0), y1 = min(2 * oy + 1, H - 1);
+    const int x0 = max(2 * ox - 1, 0), x1 = min(2 * ox + 1, W - 1);
+    const vec_t* src = reinterpret_cast<const vec_t*>(in) + (unsigned)(b * H * W) * groups + g;
+    vec_t m = __ldg(src + (unsigned)(y0 * W + x0) * groups);
+    for (int y = y0; y <= y1; ++y)
+      for (int x = x0; x <= x1; ++x) m = vmax(m, __ldg(src + (unsigned)(y * W + x) * groups), T());
+    reinterpret_cast<vec_t*>(out)[i] = m;
+  }
+}
+
+template <typename T>
+int launch_maxpool3x3s2_nhwc(const T* in, T* out, int B, int H, int W, int C, cudaStream_t st) {
+  if (B == 0) return SX_OK;
+  SX_REQUIRE(C % Elem<T>::kVec == 0, "maxpool: channels (%d) must be a multiple of %d", C, Elem<T>::kVec);
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long total = (long long)B * OH * OW * (C / Elem<T>::kVec);
+  SX_REQUIRE(total < (1ll << 31) && (long long)B * H * W * (C / Elem<T>::kVec) < (1ll << 31), "maxpool: tensor too large for 32-bit indexing");
+  maxpool3x3s2_nhwc_kernel<T><<<ew_grid(total, 256, 16), 256, 0, st>>>(in, out, B, H, W, C, OH, OW);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
 template <typename T>
 int launch_resize_aa_normalize_s2d(const float* in, T* out, int B, int IH, int IW, int OH, int OW, const Norm3& nm, cudaStream_t st) {
   if (B == 0) return SX_OK;

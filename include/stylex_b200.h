@@ -103,6 +103,12 @@ int sx_resize_aa_normalize(const float* in, void* out, int out_bf16, int B, int 
 int sx_resize_aa_normalize_s2d(const float* in, void* out, int out_bf16, int B, int IH, int IW, int OH, int OW, int normalize,
                                const float* mean3, const float* std3, sx_stream_t stream);
 
+/* torch.nn.functional.max_pool2d(x, kernel_size=3, stride=2, padding=1) on the memory of a channels_last [B,C,H,W]
+ * tensor (= [B,H,W,C]); out [B,(H-1)/2+1,(W-1)/2+1,C].  The pool between the ResNet stem and layer1 (torchvision
+ * resnet.py `self.maxpool`, reached from resnet_classifier.py:71) -- bit-identical to ATen's kernel, NaNs propagate.
+ * C must be a multiple of 8 (bf16) / 4 (fp32). */
+int sx_maxpool3x3s2_nhwc(const void* in, void* out, int is_bf16, int B, int H, int W, int C, sx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Generator plan -- sits under Generator.forward (ST:794-825) and the notebook's repeated
  * stylex.G(w, noise) calls (NB:318,382).

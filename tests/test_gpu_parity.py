@@ -416,6 +416,11 @@ def test_fused_classifier_matches_eager(dev, dtype, tol):
     got = clf.classify_images(imgs.to(dev))
     assert got.shape == ref.shape and torch.isfinite(got).all()
     assert float((got - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    clf.fused.enable_native_pool()
+    before = _native.launch_count()
+    got2 = clf.classify_images(imgs.to(dev))
+    assert _native.launch_count() - before == 1
+    assert torch.equal(got2, got)        # the native pool is bit-identical, so is everything after it
 
 
 @pytest.mark.parametrize("size", [256, 64, 224, 300])
@@ -468,6 +473,27 @@ def test_s2d_stem_matches_eager_and_native_s2d_preprocess_is_exact(dev, dtype, t
     clf.use_native_preprocess(True)
     got2 = clf.classify_images(x)                     # native space-to-depth preprocessing
     assert float((got2 - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(3, 64, 112, 112), (2, 8, 7, 9), (1, 16, 1, 1), (0, 8, 4, 4)])
+def test_native_maxpool_is_bit_identical(dev, dtype, shape):
+    """sx_maxpool3x3s2_nhwc == F.max_pool2d(x, 3, 2, 1) on channels_last tensors, bit for bit (NaNs included)."""
+    from stylex_b200.classifiers import FusedResNetInference
+    g = torch.Generator().manual_seed(shape[2])
+    x = (torch.randn(shape, generator=g) * 3).to(dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    if x.numel() > 64:
+        x[0, 5, 0, 0] = float("nan")
+        x[-1, 3, -1, -1] = float("-inf")
+    f = FusedResNetInference.__new__(FusedResNetInference)
+    f.native_pool = True
+    before = _native.launch_count()
+    got = f._pool(x)
+    assert _native.launch_count() - before == (1 if shape[0] else 0)
+    ref = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.nan_to_num(got.float(), nan=12345.0), torch.nan_to_num(ref.float(), nan=12345.0))
+    assert bool(torch.isnan(got).any()) == bool(torch.isnan(ref).any())
 
 
 def test_edge_cases_empty_and_ragged(dev):
