@@ -16,7 +16,8 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int
 import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libstylex_b200.so")
+# SX_LIB_PATH: load another build of the SAME sources (profiling builds with -DSX_HALO_DEBUG_KNOBS, A/B experiments)
+LIB_PATH = os.environ.get("SX_LIB_PATH") or os.path.join(PKG_DIR, "libstylex_b200.so")
 CSRC = os.path.join(PKG_DIR, "csrc")
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "stylex_b200.h")
 

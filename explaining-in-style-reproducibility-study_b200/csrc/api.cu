@@ -212,8 +212,9 @@ int sx_resize_aa_normalize_s2d(const float* in, void* out, int out_bf16, int B, 
 }
 
 int sx_maxpool3x3s2_nhwc(const void* in, void* out, int is_bf16, int B, int H, int W, int C, sx_stream_t stream) {
-  SX_REQUIRE(in && out, "null argument");
   SX_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 1, "bad shape");
+  if (B == 0) return SX_OK;
+  SX_REQUIRE(in && out, "null argument");
   if (is_bf16)
     return launch_maxpool3x3s2_nhwc<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, S(stream));
   return launch_maxpool3x3s2_nhwc<float>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), B, H, W, C, S(stream));

@@ -19,6 +19,9 @@
 // RESIDENT in shared memory for the CTA's lifetime; otherwise weights stream through their own ring.
 #pragma once
 
+#include <algorithm>
+#include <cstring>
+
 #include "conv_tc.cuh"
 
 namespace sx {
@@ -38,26 +41,51 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
 }
 
 // fused-upsample variant (UPS): the conv input is the LOW-RESOLUTION tensor; a 10 x 6 pixel source box per channel chunk
-// is TMA-loaded (un-swizzled) into its own ring and four producer warps write the bilinearly upsampled 18 x 10 halo box
+// is TMA-loaded (un-swizzled) into its own ring and the producer warps write the bilinearly upsampled 18 x 10 halo box
 // into the swizzled A stage (see the producer branch of the kernel).
 constexpr int UPS_SRC_W = HALO_W / 2 + 1, UPS_SRC_H = HALO_H / 2 + 1;   // 6 x 10 source pixels
 constexpr int UPS_S_STAGES = 2;
-constexpr int UPS_THREADS = 128;
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS = false>
+constexpr int halo_pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+// Warp roles: 0 = TMA producer, 1-2 = MMA issuers (1 also allocates TMEM), 3 idle, then SETS epilogue sets of four warps
+// (one TMEM lane quarter each), then (UPS) UPS_WARPS upsample producers.  The layers this kernel serves are EPILOGUE-bound, not
+// MMA-bound (Co <= 128: a 128 x 32 tile is 288 tensor cycles of MMA but ~1500 warp-instructions of epilogue), so the
+// accumulator ring has SETS slots and every slot has its own epilogue set: set s drains tiles s, s + SETS, ... while the
+// other sets drain theirs -- 4 * SETS warps hide the TMEM-load / shared-table / global-store latencies of each other.
+// Every slot holds TPS consecutive tiles (a "super-tile": same sample, same tile row, x advancing by 8): an epilogue
+// thread drains pixel r of all TPS tiles in one pass, so each per-channel table value it fetches from shared memory
+// (a broadcast LDS: 128 threads read the same word) serves TPS pixels.  ncu: with TPS = 1 those table loads were 55-60 %
+// of the shared-memory wavefronts of the narrow layers, whose L1/shared data pipe ran at 80-85 % -- the actual bound.
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS, int SETS, int UPS_WARPS, int TPS>
 struct HaloCfg {
+  static_assert(SETS >= 2 && SETS <= 4, "2..4 accumulator slots / epilogue sets");
+  static_assert(TPS == 2 || TPS == 4, "tiles per accumulator slot (even: the two MMA warps take alternate tiles)");
+  // The activation ring (and the weight ring, when weights stream) is split in two halves, one per MMA warp: even tiles
+  // go through half 0, odd tiles through half 1.  An mbarrier parity wait can only tell adjacent phases apart, so every
+  // ring needs a single in-order consumer.
+  static_assert(A_STAGES % 2 == 0 && (RESIDENT_B || B_STAGES % 2 == 0), "rings are split between the two MMA warps");
+  static constexpr int kAHalf = A_STAGES / 2, kBHalf = B_STAGES / 2;
+  static_assert(!UPS || UPS_WARPS == 4 || UPS_WARPS == 8, "4 (8 channels per thread) or 8 (4 channels per thread) producer warps");
   static constexpr int kRowBytes = BLOCK_K * 2;
-  static constexpr int kThreads = NUM_THREADS + (UPS ? UPS_THREADS : 0);
+  static constexpr int kEpiThreads = 128 * SETS;
+  static constexpr int kUpsThreads = UPS ? 32 * UPS_WARPS : 0;
+  static constexpr int kFrontThreads = 128;   // warp 0 TMA, warps 1-2 MMA issuers, warp 3 idle (keeps the sets 4-aligned)
+  static constexpr int kThreads = kFrontThreads + kEpiThreads + kUpsThreads;
   static constexpr int kSrcBytes = UPS_SRC_W * UPS_SRC_H * kRowBytes;   // one source box (7680 B at BLOCK_K = 64)
   static constexpr int kSrcRegion = UPS ? UPS_S_STAGES * kSrcBytes : 0;
   static constexpr int kATx = HALO_ROWS * kRowBytes;              // bytes one halo box delivers
   static constexpr int kABytes = (kATx + 1023) / 1024 * 1024;     // stage stride (keeps every stage 1024 B aligned)
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;           // weights of one (channel chunk, tap)
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns must be a power of two <= 512");
+  static constexpr int kSlotCols = TPS * BLOCK_N;
+  static constexpr int kTmemCols = halo_pow2_cols(SETS * kSlotCols);
+  static_assert(SETS * kSlotCols <= 512, "TMEM has 512 columns");
+  static constexpr int kBarBytes = 512;
+  static_assert((2 * A_STAGES + 2 * B_STAGES + 2 * SETS + 2 * UPS_S_STAGES) * 8 + 8 <= kBarBytes, "barrier block overflow");
+  static constexpr int kTableFloats = (2 + 10 * SETS) * BLOCK_N;  // nw, nb, then per set 2 slots x (d, m, 3 rgb rows)
   __host__ __device__ static size_t b_region(int num_b_tiles) { return (size_t)(RESIDENT_B ? num_b_tiles : B_STAGES) * kBBytes; }
   static size_t smem_bytes(int num_b_tiles) {
-    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + 256 + (size_t)(2 + 4 + 6) * BLOCK_N * sizeof(float) + kSrcRegion;
+    return 1024 + (size_t)A_STAGES * kABytes + b_region(num_b_tiles) + kBarBytes + (size_t)kTableFloats * sizeof(float) + kSrcRegion;
   }
 };
 
@@ -68,18 +96,79 @@ struct ConvHaloParams {
   int debug;                         // SX_HALO_DEBUG bitmask (bottleneck experiments; results are garbage when set):
                                      //   1 skip epilogue math/stores, 2 skip MMA issue, 4 skip activation TMA loads
   int kchunks, num_b_tiles;          // Ci/BLOCK_K, 9*kchunks
+  int tps;                           // tiles per accumulator slot actually used: min(TPS, tiles per sample), a power of two
+  unsigned long long* trace;         // SX_HALO_DEBUG_KNOBS builds: [8 roles][64 tiles] clock64 stamps of CTA (0,0); else null
   ConvEpilogue ep;
 };
 
-// resident CTAs per SM the register budget is compiled for: the narrow layers' per-tile chain (TMEM wait -> ld ->
-// math -> barrier) is latency-bound, so more independent CTAs per SM is what hides it
-template <int BLOCK_N, int BLOCK_K>
-constexpr int halo_min_ctas() { return BLOCK_N == 32 ? 2 : 1; }   // 2 CTAs/SM where smem allows it; 3 (96 regs, spills) measured slower
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS>
-__global__ void __launch_bounds__(NUM_THREADS + (UPS ? UPS_THREADS : 0), halo_min_ctas<BLOCK_N, BLOCK_K>())
+// The generator's epilogue on 4 accumulator columns of one pixel, two columns per instruction (see epi_fast32 in
+// conv_tc.cuh for the arithmetic; identical values), with the per-channel table values already in registers.
+// OUT: the modulated tensor is wanted (om), RAW: the raw one (orw).  om / orw: 2 packed bf16x2 words each.
+struct EpiTab4 {
+  float4 d, w, b, m, r0, r1, r2;
+};
+template <bool RGB, bool OUT, bool RAW>
+__device__ __forceinline__ void epi_group4(const uint32_t* __restrict__ v, const EpiTab4& t, uint64_t nz2, uint32_t* __restrict__ om,
+                                           uint32_t* __restrict__ orw, uint64_t* __restrict__ racc) {
+  const uint64_t c02 = pk2(0.2f, 0.2f);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint64_t d2 = h ? pk2(t.d.z, t.d.w) : pk2(t.d.x, t.d.y);
+    const uint64_t w2 = h ? pk2(t.w.z, t.w.w) : pk2(t.w.x, t.w.y);
+    const uint64_t b2 = h ? pk2(t.b.z, t.b.w) : pk2(t.b.x, t.b.y);
+    const uint64_t t2 = fma2(pk2(__uint_as_float(v[2 * h]), __uint_as_float(v[2 * h + 1])), d2, fma2(nz2, w2, b2));
+    const uint64_t l2 = mul2(t2, c02);
+    float t0, t1, l0, l1;
+    upk2(t2, t0, t1);
+    upk2(l2, l0, l1);
+    const uint32_t raw = bf16x2_rn(fmaxf(t0, l0), fmaxf(t1, l1));
+    if (RAW) orw[h] = raw;
+    if (OUT || RGB) {
+      const uint64_t fr2 = pk2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+      if (OUT) {
+        const uint64_t m2 = h ? pk2(t.m.z, t.m.w) : pk2(t.m.x, t.m.y);
+        float f0, f1;
+        upk2(mul2(fr2, m2), f0, f1);
+        om[h] = bf16x2_rn(f0, f1);
+      }
+      if (RGB) {
+        racc[0] = fma2(fr2, h ? pk2(t.r0.z, t.r0.w) : pk2(t.r0.x, t.r0.y), racc[0]);
+        racc[1] = fma2(fr2, h ? pk2(t.r1.z, t.r1.w) : pk2(t.r1.x, t.r1.y), racc[1]);
+        racc[2] = fma2(fr2, h ? pk2(t.r2.z, t.r2.w) : pk2(t.r2.x, t.r2.y), racc[2]);
+      }
+    }
+  }
+}
+
+// bf16x2 word -> packed fp32x2 (exact)
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return bf16x2_rn(lo, hi);
+}
+
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS, int SETS, int UPS_WARPS,
+          int TPS, int MIN_CTAS>
+__global__ void __launch_bounds__(HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS>::kThreads, MIN_CTAS)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvHaloParams p) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS>;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS>;
   static_assert(!UPS || BLOCK_K == 64, "the fused-upsample producer writes the SWIZZLE_128B layout");
   extern __shared__ uint8_t smem_raw[];
   // offset arithmetic on the __shared__ array (not an integer round trip) keeps the shared address space known to the
@@ -92,18 +181,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* a_empty = a_full + A_STAGES;
   uint64_t* b_full = a_empty + A_STAGES;          // [B_STAGES]  (resident: b_full[0] = "all weights landed")
   uint64_t* b_empty = b_full + B_STAGES;
-  uint64_t* tmem_full = b_empty + B_STAGES;       // [2]
-  uint64_t* tmem_empty = tmem_full + 2;           // [2]
-  uint64_t* s_full = tmem_empty + 2;              // [UPS_S_STAGES]  (UPS only) source box landed
+  uint64_t* tmem_full = b_empty + B_STAGES;       // [SETS]
+  uint64_t* tmem_empty = tmem_full + SETS;        // [SETS]
+  uint64_t* s_full = tmem_empty + SETS;           // [UPS_S_STAGES]  (UPS only) source box landed
   uint64_t* s_empty = s_full + UPS_S_STAGES;      // [UPS_S_STAGES]  (UPS only) producers are done with the source box
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_empty + UPS_S_STAGES);
-  static_assert((2 * A_STAGES + 2 * B_STAGES + 4 + 2 * UPS_S_STAGES) * 8 + 8 <= 256, "barrier block overflow");
-  float* s_nw = reinterpret_cast<float*>(after + 256);
+  float* s_nw = reinterpret_cast<float*>(after + Cfg::kBarBytes);
   float* s_nb = s_nw + BLOCK_N;
-  float* s_d = s_nb + BLOCK_N;            // [2][BLOCK_N] demod coefficients of the tile's sample (per accumulator slot)
-  float* s_m = s_d + 2 * BLOCK_N;         // [2][BLOCK_N] next-layer (style+1)
-  float* s_rgbw = s_m + 2 * BLOCK_N;      // [2][3][BLOCK_N] fused-ToRGB weights of the tile's sample
-  uint8_t* smem_src = reinterpret_cast<uint8_t*>(s_rgbw + 6 * BLOCK_N);   // (UPS only) [UPS_S_STAGES][10][6][BLOCK_K] bf16
+  float* s_tab = s_nb + BLOCK_N;          // [SETS][2 slots][d | m | rgb0 | rgb1 | rgb2][BLOCK_N]
+  uint8_t* smem_src = reinterpret_cast<uint8_t*>(s_nw + Cfg::kTableFloats);   // (UPS only) [UPS_S_STAGES][10][6][BLOCK_K] bf16
 
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,21 +197,37 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // Each CTA walks a CONTIGUOUS range of tiles (sample-major, then rows, then columns): the tile's sample -- and with it
   // the per-sample epilogue tables -- changes once per several hundred tiles instead of every other tile, and
   // consecutive tiles share halo columns in L2.
-  const int tile_begin = (int)((long long)blockIdx.x * p.num_tiles / gridDim.x);
-  const int tile_end = (int)((long long)(blockIdx.x + 1) * p.num_tiles / gridDim.x);
+  // The unit of the walk is the super-tile (tps tiles: one accumulator slot).
+  const int tps = p.tps;
+  const int num_super = p.num_tiles / tps;
+  const int super_begin = (int)((long long)blockIdx.x * num_super / gridDim.x);
+  const int super_end = (int)((long long)(blockIdx.x + 1) * num_super / gridDim.x);
+  const int tile_begin = super_begin * tps, tile_end = super_end * tps;
 #ifdef SX_HALO_DEBUG_KNOBS   // bottleneck experiments only (profiles/README.md); never in the shipped library
   const int dbg = p.debug;
 #else
   constexpr int dbg = 0;
 #endif
+#ifdef SX_HALO_DEBUG_KNOBS
+#define SX_TRACE(role, idx)                                                                          \
+  do {                                                                                               \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) >= 0 && (idx) < 64) p.trace[(role) * 64 + (idx)] = clock64(); \
+  } while (0)
+#else
+#define SX_TRACE(role, idx) do { } while (0)
+#endif
 
+  for (int i = threadIdx.x; i < BLOCK_N; i += Cfg::kThreads) {
+    s_nw[i] = p.ep.noise ? __ldg(p.ep.noise_w + n0 + i) : 0.f;
+    s_nb[i] = p.ep.noise ? __ldg(p.ep.noise_b + n0 + i) : 0.f;
+  }
   if (warp_id == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], UPS ? UPS_THREADS : 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], UPS ? Cfg::kUpsThreads : 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
-    if (UPS) for (int s = 0; s < UPS_S_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], UPS_THREADS); }
+    for (int s = 0; s < SETS; ++s) { mbar_init(&tmem_full[s], 2); mbar_init(&tmem_empty[s], 128); }   // full: one commit per MMA warp
+    if (UPS) for (int s = 0; s < UPS_S_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], Cfg::kUpsThreads); }
     fence_barrier_init();
   } else if (warp_id == 1) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
@@ -148,71 +250,102 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __syncwarp();
       }
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      // ring positions per half (index = tile parity); the source-box ring of the fused upsample is one in-order ring
+      int as2[2] = {0, 0}, bs2[2] = {0, 0}, ss = 0;
+      uint32_t aph2[2] = {0, 0}, bph2[2] = {0, 0}, sph = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int b = tile >> p.tpb_shift;
         const int tr = tile - (b << p.tpb_shift);
         const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
         const int x0 = tx * HALO_BW, y0 = ty * HALO_BH;
+        const int rg = (tile - tile_begin) & 1;
+        int as = rg ? as2[1] : as2[0], bs = rg ? bs2[1] : bs2[0];
+        uint32_t aph = rg ? aph2[1] : aph2[0], bph = rg ? bph2[1] : bph2[0];
         for (int chunk = 0; chunk < p.kchunks; ++chunk) {
           if (UPS) {
             // low-resolution source box of the halo box: rows y0/2-1 .. y0/2+8, columns x0/2-1 .. x0/2+4 (zero-filled
             // outside the image; the producers clamp instead, like torch's bilinear kernel)
-            mbar_wait(&s_empty[as], aph ^ 1, 10);
+            mbar_wait(&s_empty[ss], sph ^ 1, 10);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&s_full[as], Cfg::kSrcBytes);
-              tma_load_4d(smem_src + as * Cfg::kSrcBytes, &tmap_a, &s_full[as], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
+              if (chunk == 0) SX_TRACE(0, tile - tile_begin);
+              mbar_arrive_expect_tx(&s_full[ss], Cfg::kSrcBytes);
+              tma_load_4d(smem_src + ss * Cfg::kSrcBytes, &tmap_a, &s_full[ss], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
             }
             __syncwarp();
-            if (++as == UPS_S_STAGES) { as = 0; aph ^= 1; }
+            if (++ss == UPS_S_STAGES) { ss = 0; sph ^= 1; }
           } else {
-            mbar_wait(&a_empty[as], aph ^ 1, 10);
+            const int st = rg * Cfg::kAHalf + as;
+            mbar_wait(&a_empty[st], aph ^ 1, 10);
             if (elect_one()) {
+              if (chunk == 0) SX_TRACE(0, tile - tile_begin);
               if (dbg & 4) {
-                mbar_arrive(&a_full[as]);
+                mbar_arrive(&a_full[st]);
               } else {
-                mbar_arrive_expect_tx(&a_full[as], Cfg::kATx);
-                tma_load_4d(smem_a + as * Cfg::kABytes, &tmap_a, &a_full[as], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+                mbar_arrive_expect_tx(&a_full[st], Cfg::kATx);
+                tma_load_4d(smem_a + st * Cfg::kABytes, &tmap_a, &a_full[st], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
               }
             }
             __syncwarp();
-            if (++as == A_STAGES) { as = 0; aph ^= 1; }
+            if (++as == Cfg::kAHalf) { as = 0; aph ^= 1; }
           }
           if (!RESIDENT_B) {
 #pragma unroll 1
             for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&b_empty[bs], bph ^ 1, 11);
+              const int st = rg * Cfg::kBHalf + bs;
+              mbar_wait(&b_empty[st], bph ^ 1, 11);
               if (elect_one()) {
-                mbar_arrive_expect_tx(&b_full[bs], Cfg::kBBytes);
-                tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmap_b, &b_full[bs], tap * p.Ci + chunk * BLOCK_K, n0);
+                mbar_arrive_expect_tx(&b_full[st], Cfg::kBBytes);
+                tma_load_2d(smem_b + st * Cfg::kBBytes, &tmap_b, &b_full[st], tap * p.Ci + chunk * BLOCK_K, n0);
               }
               __syncwarp();
-              if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+              if (++bs == Cfg::kBHalf) { bs = 0; bph ^= 1; }
             }
           }
         }
+        if (rg) { as2[1] = as; aph2[1] = aph; bs2[1] = bs; bph2[1] = bph; }
+        else { as2[0] = as; aph2[0] = aph; bs2[0] = bs; bph2[0] = bph; }
       }
     }
-  } else if (warp_id == 1) {
-    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+  } else if (warp_id == 1 || warp_id == 2) {
+    // ===================== MMA issuers (two warps; warp-uniform control flow, one elected lane issues) =====================
+    // Pipeline traces (profiles/README.md) showed ONE issuing warp pacing every layer this kernel serves: tcgen05.mma issue
+    // blocks while the (short) MMA queue is full, so the warp spends the tile's whole MMA time inside the issue loop and
+    // only then runs its per-tile bookkeeping (barrier waits, fences, descriptors: 500-1000 cycles of dependent scalar
+    // code) with the tensor pipe idle -- ~38 % of the cadence.  Two warps take alternate tiles: while one is blocked
+    // issuing, the other does its bookkeeping, and the queue never drains.  Ring positions are functions of the tile
+    // index, so neither warp needs the other's state; both commit to the slot's tmem_full barrier (count 2).
     {
+      const int mw = warp_id - 1;
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       constexpr uint32_t sbo = HALO_W * Cfg::kRowBytes;
       if (RESIDENT_B) {
         mbar_wait(&b_full[0], 0, 12);
         tc_fence_after();
       }
-      int as = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, accph = 0;
-      const uint32_t a_base0 = smem_u32(smem_a), b_base0 = smem_u32(smem_b);
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int chunk = 0; chunk < p.kchunks; ++chunk) {
-          mbar_wait(&a_full[as], aph, 14);
+      const uint32_t a_base0 = smem_u32(smem_a) + (uint32_t)(mw * Cfg::kAHalf * Cfg::kABytes);   // this warp's half of the A ring
+      const uint32_t b_base0 = smem_u32(smem_b) + (RESIDENT_B ? 0u : (uint32_t)(mw * Cfg::kBHalf * Cfg::kBBytes));
+      uint64_t* my_a_full = a_full + mw * Cfg::kAHalf;
+      uint64_t* my_a_empty = a_empty + mw * Cfg::kAHalf;
+      uint64_t* my_b_full = b_full + (RESIDENT_B ? 0 : mw * Cfg::kBHalf);
+      uint64_t* my_b_empty = b_empty + (RESIDENT_B ? 0 : mw * Cfg::kBHalf);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const int tps_shift = tps == 4 ? 2 : 1;        // tps is 2 or 4
+      for (int tile = tile_begin + mw; tile < tile_end; tile += 2) {
+        const int ti = tile - tile_begin;
+        const int si = ti >> tps_shift, sub = ti - (si << tps_shift);
+        const int acc = si % SETS;
+        const uint32_t accph = (uint32_t)(si / SETS) & 1u;
+        if (sub < 2) {   // this warp's first tile of the super-tile
+          mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // this slot's epilogue set has drained the accumulators
           tc_fence_after();
+        }
+        if (lane == 0) SX_TRACE(1, ti);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kSlotCols + sub * BLOCK_N);
+        for (int chunk = 0; chunk < p.kchunks; ++chunk) {
+          mbar_wait(&my_a_full[as], aph, 14);
+          tc_fence_after();
+          if (lane == 0 && chunk == 0) SX_TRACE(2, ti);
           // descriptors of tap 0; every other tap / k step is this plus a compile-time constant (fully unrolled)
           const uint64_t da0 = make_smem_desc_sbo<BLOCK_K>(a_base0 + (uint32_t)(as * Cfg::kABytes), sbo);
           const uint64_t db_res = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(chunk * 9 * Cfg::kBBytes));
@@ -235,7 +368,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&b_full[bs], bph, 15);
+              mbar_wait(&my_b_full[bs], bph, 15);
               tc_fence_after();
               const uint64_t db = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(bs * Cfg::kBBytes));
               const int ky = tap / 3, kx = tap - ky * 3;
@@ -246,40 +379,50 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                     umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(&b_empty[bs]);
+                umma_commit(&my_b_empty[bs]);
               }
               __syncwarp();
-              if (++bs == B_STAGES) { bs = 0; bph ^= 1; }
+              if (++bs == Cfg::kBHalf) { bs = 0; bph ^= 1; }
             }
           }
-          if (elect_one()) umma_commit(&a_empty[as]);
+          if (elect_one()) umma_commit(&my_a_empty[as]);
           __syncwarp();
-          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (++as == Cfg::kAHalf) { as = 0; aph ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
-        __syncwarp();
-        acc ^= 1;
-        if (acc == 0) accph ^= 1;
+        if (lane == 0) SX_TRACE(3, ti);
+        if (sub + 2 >= tps) {   // this warp's last tile of the super-tile: its half of the hand-over to the epilogue set
+          if (elect_one()) umma_commit(&tmem_full[acc]);
+          __syncwarp();
+        }
       }
     }
-  } else if (UPS && warp_id >= 6) {
-    // ===================== fused bilinear 2x upsample: A-operand producers (warps 6..9) =====================
+  } else if (UPS && warp_id >= 4 + 4 * SETS) {
+    // ===================== fused bilinear 2x upsample: A-operand producers =====================
     // out halo pixel (hy, hx) <-> image pixel (y0-1+hy, x0-1+hx); y0, x0 are even, so halo rows (2k, 2k+1) interpolate
     // source-box rows (k, k+1) with weights (.75,.25) / (.25,.75) (align_corners=False, scale 2: src = o/2 - 0.25),
     // and likewise for columns.  Source indices are clamped to the image (torch's border rule); halo pixels outside
-    // the image are the conv's zero padding.  Thread = one 16-byte channel group x one column pair x one third of
-    // the rows; horizontal pass per source row, then the vertical pass, all in fp32, one rounding to bf16.
-    const int pt = threadIdx.x - NUM_THREADS;   // 0..127
-    const int cg = pt & 7;
-    const int unit = pt >> 3;                   // 0..15; unit 15 has no work
+    // the image are the conv's zero padding.  Thread = one channel group (CH channels) x one column pair x one third of
+    // the rows; horizontal pass per source row, then the vertical pass, all in (packed) fp32, one rounding to bf16.
+    constexpr int CH = UPS_WARPS == 4 ? 8 : 4;      // channels per thread
+    constexpr int NW = CH / 2;                      // bf16x2 words per thread
+    constexpr int CGS = 64 / CH;                    // channel groups per pixel row
+    const int pt = threadIdx.x - (Cfg::kFrontThreads + Cfg::kEpiThreads);
+    const int cg = pt % CGS;
+    const int unit = pt / CGS;                  // 0..15; unit 15 has no work
     const int j = unit % 5;                     // halo columns 2j, 2j+1 <- source columns j, j+1
     const int seg = unit / 5;                   // halo rows 6seg .. 6seg+5 <- source rows 3seg .. 3seg+3
-    int as = 0, ss = 0;
-    uint32_t aph = 0, sph = 0;
+    const uint32_t cbyte = (uint32_t)(cg * CH * 2);            // byte offset of the channel group inside a 128-byte pixel row
+    const uint32_t c16 = cbyte >> 4, cin = cbyte & 15u;        // 16-byte chunk index (swizzled), offset inside the chunk
+    const uint64_t q25 = pk2(0.25f, 0.25f), q75 = pk2(0.75f, 0.75f);
+    int as2[2] = {0, 0}, ss = 0;     // A-ring position per half (tile parity), one in-order source-box ring
+    uint32_t aph2[2] = {0, 0}, sph = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int b = tile >> p.tpb_shift;
       const int tr = tile - (b << p.tpb_shift);
       const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
+      const int rg = (tile - tile_begin) & 1;
+      int as = rg ? as2[1] : as2[0];
+      uint32_t aph = rg ? aph2[1] : aph2[0];
       const bool left = tx == 0, right = tx == p.tiles_x - 1, top = ty == 0, bottom = ty == p.tiles_y - 1;
       const int lo_c = left ? 1 : 0, hi_c = right ? UPS_SRC_W - 2 : UPS_SRC_W - 1;
       const int lo_r = top ? 1 : 0, hi_r = bottom ? UPS_SRC_H - 2 : UPS_SRC_H - 1;
@@ -287,29 +430,42 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const bool zero_e = left && j == 0;        // halo column 0 is outside the image
       const bool zero_o = right && j == 4;       // halo column 9 is outside the image
       for (int chunk = 0; chunk < p.kchunks; ++chunk) {
+        const int st = rg * Cfg::kAHalf + as;
         mbar_wait(&s_full[ss], sph, 17);
-        mbar_wait(&a_empty[as], aph ^ 1, 18);
+        mbar_wait(&a_empty[st], aph ^ 1, 18);
         if (seg < 3) {
-          const uint8_t* src = smem_src + ss * Cfg::kSrcBytes + cg * 16;
-          uint8_t* dst = smem_a + as * Cfg::kABytes;
-          float he0[8], ho0[8], he1[8], ho1[8];
-          auto hrow = [&](int r, float* he, float* ho) {
-            const int rr = min(max(r, lo_r), hi_r);
-            float a[8], c[8];
-            unpack(*reinterpret_cast<const uint4*>(src + (rr * UPS_SRC_W + c0) * Cfg::kRowBytes), a);
-            unpack(*reinterpret_cast<const uint4*>(src + (rr * UPS_SRC_W + c1) * Cfg::kRowBytes), c);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              he[k] = fmaf(0.25f, c[k], 0.75f * a[k]);   // odd image column 2m+1
-              ho[k] = fmaf(0.75f, c[k], 0.25f * a[k]);   // even image column 2m+2
+          const uint8_t* src = smem_src + ss * Cfg::kSrcBytes + cbyte;
+          uint8_t* dst = smem_a + st * Cfg::kABytes + cin;
+          uint64_t he0[NW], ho0[NW], he1[NW], ho1[NW];
+          auto ldv = [&](const uint8_t* ptr, uint32_t* w) {
+            if constexpr (CH == 8) {
+              const uint4 t = *reinterpret_cast<const uint4*>(ptr);
+              w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+            } else {
+              const uint2 t = *reinterpret_cast<const uint2*>(ptr);
+              w[0] = t.x; w[1] = t.y;
             }
           };
-          auto put = [&](int hy, int hx, const float* v, bool zero) {
+          auto hrow = [&](int r, uint64_t* he, uint64_t* ho) {
+            const int rr = min(max(r, lo_r), hi_r);
+            uint32_t a[NW], c[NW];
+            ldv(src + (rr * UPS_SRC_W + c0) * Cfg::kRowBytes, a);
+            ldv(src + (rr * UPS_SRC_W + c1) * Cfg::kRowBytes, c);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+              const uint64_t a2 = bf2_to_f2(a[k]), c2 = bf2_to_f2(c[k]);
+              he[k] = fma2(q25, c2, mul2(q75, a2));   // odd image column 2m+1
+              ho[k] = fma2(q75, c2, mul2(q25, a2));   // even image column 2m+2
+            }
+          };
+          auto put = [&](int hy, int hx, const uint64_t* v, bool zero) {
             const int pix = hy * HALO_W + hx;
-            uint4 pk;
-            if (zero) pk = make_uint4(0u, 0u, 0u, 0u);
-            else pack(v, pk);
-            *reinterpret_cast<uint4*>(dst + pix * Cfg::kRowBytes + ((cg ^ (pix & 7)) << 4)) = pk;
+            uint32_t w[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = zero ? 0u : f2_to_bf2(v[k]);
+            uint8_t* d = dst + pix * Cfg::kRowBytes + ((c16 ^ (uint32_t)(pix & 7)) << 4);
+            if constexpr (CH == 8) *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+            else *reinterpret_cast<uint2*>(d) = make_uint2(w[0], w[1]);
           };
           hrow(3 * seg, he0, ho0);
 #pragma unroll
@@ -318,43 +474,46 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             hrow(k + 1, he1, ho1);
             const bool zt = top && k == 0;        // halo row 0 is outside the image
             const bool zb = bottom && k == 8;     // halo row 17 is outside the image
-            float v[8];
+            uint64_t v[NW];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.25f, he1[q], 0.75f * he0[q]);
+            for (int q = 0; q < NW; ++q) v[q] = fma2(q25, he1[q], mul2(q75, he0[q]));
             put(2 * k, 2 * j, v, zt || zero_e);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.25f, ho1[q], 0.75f * ho0[q]);
+            for (int q = 0; q < NW; ++q) v[q] = fma2(q25, ho1[q], mul2(q75, ho0[q]));
             put(2 * k, 2 * j + 1, v, zt || zero_o);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.75f, he1[q], 0.25f * he0[q]);
+            for (int q = 0; q < NW; ++q) v[q] = fma2(q75, he1[q], mul2(q25, he0[q]));
             put(2 * k + 1, 2 * j, v, zb || zero_e);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaf(0.75f, ho1[q], 0.25f * ho0[q]);
+            for (int q = 0; q < NW; ++q) v[q] = fma2(q75, ho1[q], mul2(q25, ho0[q]));
             put(2 * k + 1, 2 * j + 1, v, zb || zero_o);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { he0[q] = he1[q]; ho0[q] = ho1[q]; }
+            for (int q = 0; q < NW; ++q) { he0[q] = he1[q]; ho0[q] = ho1[q]; }
           }
         }
         // generic-proxy writes -> visible to the async proxy (tcgen05.mma reads shared memory through it)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&a_full[as]);
+        mbar_arrive(&a_full[st]);
         mbar_arrive(&s_empty[ss]);
-        if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        if (pt == 0 && chunk == 0) SX_TRACE(7, tile - tile_begin);
+        if (++as == Cfg::kAHalf) { as = 0; aph ^= 1; }
         if (++ss == UPS_S_STAGES) { ss = 0; sph ^= 1; }
       }
+      if (rg) { as2[1] = as; aph2[1] = aph; } else { as2[0] = as; aph2[0] = aph; }
     }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
+  } else if (warp_id >= 4) {
+    // ===================== epilogue: SETS sets of four warps, set s drains accumulator slot s =====================
     const ConvEpilogue& ep = p.ep;
-    const int et = threadIdx.x - 64;  // 0..127
-    for (int i = et; i < BLOCK_N; i += 128) {
-      s_nw[i] = ep.noise ? __ldg(ep.noise_w + n0 + i) : 0.f;
-      s_nb[i] = ep.noise ? __ldg(ep.noise_b + n0 + i) : 0.f;
-    }
+    const int set = (warp_id - 4) >> 2;
+    const int et = (int)threadIdx.x - Cfg::kFrontThreads - set * 128;   // 0..127 inside the set
     const int q = warp_id & 3;          // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;        // tile row = TMEM lane
     const int yy = r >> 3, xx = r & 7;
-    int acc = 0;
+    float* tab = s_tab + set * (10 * BLOCK_N);
+    const uint32_t bar_id = 1u + (uint32_t)set;
+    const uint32_t HW = (uint32_t)(p.H * p.W);
+    const uint32_t S = (uint32_t)ep.noise_size;
+    constexpr bool fuse_rgb = FUSE_RGB;   // compile-time: the plain instantiation carries none of the ToRGB registers
     uint32_t accph = 0;
     auto tile_coords = [&](int tile, int& b, int& x, int& y) {
       b = tile >> p.tpb_shift;
@@ -363,145 +522,221 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       x = tx * HALO_BW + xx;
       y = ty * HALO_BH + yy;
     };
+    // 32-bit element offsets (the launcher checks every tensor is below 2^31 elements)
     auto load_noise = [&](int b, int x, int y) -> float {
       if (!ep.noise) return 0.f;
-      const int S = ep.noise_size;
-      return __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
+      return __ldg(ep.noise + ((ep.noise_batch == 1 ? 0u : (uint32_t)b * S * S) + (uint32_t)x * S + (uint32_t)y));
     };
-    constexpr bool fuse_rgb = FUSE_RGB;   // compile-time: the plain instantiation carries none of the ToRGB registers
-    const long long HWl = (long long)p.H * p.W;
+    auto rgb_off = [&](int b, int x, int y) -> uint32_t { return ((uint32_t)b * 3u * (uint32_t)p.H + (uint32_t)y) * (uint32_t)p.W + (uint32_t)x; };
     auto load_rgb_prev = [&](int b, int x, int y, float* v) {
       v[0] = v[1] = v[2] = 0.f;
       if (fuse_rgb && ep.rgb_accumulate) {
-        const float* src = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = __ldg(src + c * HWl);
+        const float* src = ep.rgb_out + rgb_off(b, x, y);
+        v[0] = __ldg(src);
+        v[1] = __ldg(src + HW);
+        v[2] = __ldg(src + 2u * HW);
       }
     };
-    // per-sample tables (demod coefficients, next-layer style + 1, fused-ToRGB weights) live in two shared-memory slots;
-    // a sample change (rare: tiles are walked sample-major) fills the other slot and synchronises the four warps once
+    // per-sample tables (demod coefficients, next-layer style + 1, fused-ToRGB weights) live in two slots per set;
+    // a sample change (rare: tiles are walked sample-major) fills the other slot and synchronises the set's four warps once
     auto write_tables = [&](int slot, int b) {
+      float* t = tab + slot * (5 * BLOCK_N);
       for (int i = et; i < BLOCK_N; i += 128) {
-        s_d[slot * BLOCK_N + i] = ep.dcoef ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + i) : 1.f;
-        s_m[slot * BLOCK_N + i] = ep.next_style ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) + 1.f : 1.f;
+        t[i] = ep.dcoef ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + i) : 1.f;
+        t[BLOCK_N + i] = ep.next_style ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + i) + 1.f : 1.f;
       }
       if (fuse_rgb) {
         for (int i = et; i < 3 * BLOCK_N; i += 128) {
           const int o = i % BLOCK_N;
-          s_rgbw[slot * 3 * BLOCK_N + i] =
-              (__ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o);
+          t[2 * BLOCK_N + i] = (__ldg(ep.rgb_style + (long long)b * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o);
         }
       }
     };
     // the generator's configuration (activation on, bf16 NHWC or no feature-map output) takes the packed fast path
     const bool fast = ep.act != 0 && !ep.out_nchw_f32;
+    const bool has_out = ep.out != nullptr, has_raw = ep.out_raw != nullptr;
+    // pixel j of this thread in the super-tile: same sample, same row, x advancing by 8 per tile
+    int sup = super_begin + set;
     int b = 0, x = 0, y = 0, cur_b = -1, slot = 1;
-    float nz = 0.f, rgbp[3] = {0.f, 0.f, 0.f};
-    if (tile_begin < tile_end) {
-      tile_coords(tile_begin, b, x, y);
-      nz = load_noise(b, x, y);
-      load_rgb_prev(b, x, y, rgbp);
+    float nz[TPS];
+    auto load_noises = [&](int b_, int x_, int y_, float* nzv) {
+#pragma unroll
+      for (int j = 0; j < TPS; ++j) nzv[j] = j < tps ? load_noise(b_, x_ + HALO_BW * j, y_) : 0.f;
+    };
+    if (sup < super_end) {
+      tile_coords(sup * tps, b, x, y);
+      load_noises(b, x, y, nz);
     }
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (; sup < super_end; sup += SETS) {
       if (b != cur_b) {
         slot ^= 1;
         write_tables(slot, b);
         cur_b = b;
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // tables (and, the first time, s_nw / s_nb) visible to all four warps
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // tables visible to the set's four warps
       }
-      const float* dd = s_d + slot * BLOCK_N;
-      const float* mm = s_m + slot * BLOCK_N;
-      const float* rw = s_rgbw + slot * 3 * BLOCK_N;
-      const long long pix = ((long long)b * p.H + y) * p.W + x;
-      // prefetch the next tile's per-pixel operands (consumed after this tile's TMEM drain)
+      const float* dd = tab + slot * (5 * BLOCK_N);
+      const float* mm = dd + BLOCK_N;
+      const float* rw = dd + 2 * BLOCK_N;
+      const uint32_t pix = ((uint32_t)b * (uint32_t)p.H + (uint32_t)y) * (uint32_t)p.W + (uint32_t)x;
+      const uint32_t roff = rgb_off(b, x, y);
+      // prefetch the next super-tile's noise values (consumed after this one's TMEM drain); the previous rgb of THIS
+      // super-tile is only needed at the very end (rgb = prev + sum), so its loads fly during the math
       int b2 = b, x2 = 0, y2 = 0;
-      float nz2 = 0.f, rgbp2[3] = {0.f, 0.f, 0.f};
-      if (tile + 1 < tile_end) {
-        tile_coords(tile + 1, b2, x2, y2);
-        nz2 = load_noise(b2, x2, y2);
-        load_rgb_prev(b2, x2, y2, rgbp2);
+      float nzn[TPS];
+      if (sup + SETS < super_end) {
+        tile_coords((sup + SETS) * tps, b2, x2, y2);
+        load_noises(b2, x2, y2, nzn);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TPS; ++j) nzn[j] = 0.f;
       }
-      mbar_wait(&tmem_full[acc], accph, 16);
+      float rgb_acc[TPS][3];   // starts as the previous rgb, ends as the result
+#pragma unroll
+      for (int j = 0; j < TPS; ++j) {
+        rgb_acc[j][0] = rgb_acc[j][1] = rgb_acc[j][2] = 0.f;
+        if (j < tps) load_rgb_prev(b, x + HALO_BW * j, y, rgb_acc[j]);
+      }
+      if (et == 0) SX_TRACE(6, sup - super_begin);
+      mbar_wait(&tmem_full[set], accph, 16);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      float rgb_acc[3] = {rgbp[0], rgbp[1], rgbp[2]};
+      if (et == 0) SX_TRACE(4, sup - super_begin);
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * Cfg::kSlotCols);
       if (dbg & 1) {
       } else if (fast) {
-        constexpr int NCH = BLOCK_N / 32;
-        uint32_t v[NCH > 1 ? 2 : 1][32];
-        uint64_t racc[3] = {pk2(rgbp[0], 0.f), pk2(rgbp[1], 0.f), pk2(rgbp[2], 0.f)};
-        tmem_ld32(tbase, v[0]);
+        uint64_t racc[TPS][3];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          const int c0 = ch * 32;
-          tmem_ld_wait();
-          if (ch + 1 < NCH) tmem_ld32(tbase + (uint32_t)(c0 + 32), v[(ch + 1) & 1]);   // next chunk in flight during the math
-          uint32_t om[16], orw[16];
-          epi_fast32<fuse_rgb>(v[ch & 1], dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, om, orw, rw + c0, BLOCK_N, racc);
-          if (ep.out) {
-            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0);
+        for (int j = 0; j < TPS; ++j) racc[j][0] = racc[j][1] = racc[j][2] = 0ull;
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out) + ((size_t)pix * (uint32_t)p.Co + (uint32_t)n0);
+        __nv_bfloat16* rawp = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + ((size_t)pix * (uint32_t)p.Co + (uint32_t)n0);
+        const uint32_t jstride = (uint32_t)(HALO_BW * p.Co);   // elements between this thread's pixels of consecutive tiles
+        constexpr int CW = TPS == 4 ? 8 : 16;   // columns per pass: bounds the live registers (v, om, orw scale with TPS * CW)
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
+          uint32_t v[TPS][CW];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = make_uint4(om[4 * k], om[4 * k + 1], om[4 * k + 2], om[4 * k + 3]);
+          for (int j = 0; j < TPS; ++j) {
+            if (j < tps) {
+              if constexpr (CW == 16) tmem_ld16(tbase + (uint32_t)(j * BLOCK_N + c0), v[j]);
+              else tmem_ld8(tbase + (uint32_t)(j * BLOCK_N + c0), v[j]);
+            }
           }
-          if (ep.out_raw) {
-            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0);
+          tmem_ld_wait();
+          uint32_t om[TPS][CW / 2], orw[TPS][CW / 2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = make_uint4(orw[4 * k], orw[4 * k + 1], orw[4 * k + 2], orw[4 * k + 3]);
+          for (int g = 0; g < CW / 4; ++g) {
+            const int c = c0 + 4 * g;
+            EpiTab4 t;
+            t.d = *reinterpret_cast<const float4*>(dd + c);
+            t.w = *reinterpret_cast<const float4*>(s_nw + c);
+            t.b = *reinterpret_cast<const float4*>(s_nb + c);
+            t.m = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (has_out) t.m = *reinterpret_cast<const float4*>(mm + c);
+            t.r0 = t.r1 = t.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fuse_rgb) {
+              t.r0 = *reinterpret_cast<const float4*>(rw + c);
+              t.r1 = *reinterpret_cast<const float4*>(rw + BLOCK_N + c);
+              t.r2 = *reinterpret_cast<const float4*>(rw + 2 * BLOCK_N + c);
+            }
+#pragma unroll
+            for (int j = 0; j < TPS; ++j) {
+              if (j < tps) {
+                if (has_out) {
+                  if (has_raw) epi_group4<fuse_rgb, true, true>(v[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
+                  else epi_group4<fuse_rgb, true, false>(v[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
+                } else {
+                  epi_group4<fuse_rgb, false, false>(v[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
+                }
+              }
+            }
+          }
+          if (has_out) {
+#pragma unroll
+            for (int j = 0; j < TPS; ++j) {
+              if (j < tps) {
+                uint4* o4 = reinterpret_cast<uint4*>(outp + (size_t)j * jstride + c0);
+                uint4* r4 = reinterpret_cast<uint4*>(rawp + (size_t)j * jstride + c0);
+#pragma unroll
+                for (int k = 0; k < CW / 8; ++k) {
+                  o4[k] = make_uint4(om[j][4 * k], om[j][4 * k + 1], om[j][4 * k + 2], om[j][4 * k + 3]);
+                  if (has_raw) r4[k] = make_uint4(orw[j][4 * k], orw[j][4 * k + 1], orw[j][4 * k + 2], orw[j][4 * k + 3]);
+                }
+              }
+            }
           }
         }
         if (fuse_rgb) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float lo, hi;
-            upk2(racc[c], lo, hi);
-            rgb_acc[c] = lo + hi;
+          for (int j = 0; j < TPS; ++j) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float lo, hi;
+              upk2(racc[j][c], lo, hi);
+              rgb_acc[j][c] += lo + hi;
+            }
           }
         }
       } else {
+        // generic configuration (module-level Conv2DMod in bf16: no activation and / or NCHW fp32 output), 8 columns a time
+#pragma unroll
+        for (int j = 0; j < TPS; ++j) {
+          if (j >= tps) break;
+          const int xj = x + HALO_BW * j;
+          const size_t pixj = (size_t)pix + (size_t)(HALO_BW * j);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)c0, v);
-          tmem_ld_wait();
-          float f[32], fr[32];
-          epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
-          if (fuse_rgb) rgb_chunk32(fr, rw + c0, BLOCK_N, rgb_acc);
-          if (!ep.out) {
-          } else if (ep.out_nchw_f32) {
-            float* out = reinterpret_cast<float*>(ep.out);
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
+            uint32_t v[8];
+            tmem_ld8(tbase + (uint32_t)(j * BLOCK_N + c0), v);
+            tmem_ld_wait();
+            float f[8], fr[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
-          } else {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+            for (int k = 0; k < 8; ++k) {
+              float t = __uint_as_float(v[k]) * dd[c0 + k];
+              t += nz[j] * s_nw[c0 + k] + s_nb[c0 + k];
+              if (ep.act) t = lrelu02(t);
+              if (!ep.out_nchw_f32) t = __bfloat162float(__float2bfloat16_rn(t));
+              fr[k] = t;
+              f[k] = t * mm[c0 + k];
+              if (fuse_rgb) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              pack(f + j, pk);
-              *reinterpret_cast<uint4*>(out + j) = pk;
+                for (int c = 0; c < 3; ++c) rgb_acc[j][c] = fmaf(t, rw[c * BLOCK_N + c0 + k], rgb_acc[j][c]);
+              }
             }
-          }
-          if (ep.out_raw) {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+            if (!ep.out) {
+            } else if (ep.out_nchw_f32) {
+              float* out = reinterpret_cast<float*>(ep.out);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+              for (int k = 0; k < 8; ++k) out[(((size_t)b * p.Co + n0 + c0 + k) * p.H + y) * p.W + xj] = f[k];
+            } else {
               uint4 pk;
-              pack(fr + j, pk);
-              *reinterpret_cast<uint4*>(out + j) = pk;
+              pack(f, pk);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (pixj * p.Co + n0 + c0)) = pk;
+            }
+            if (ep.out_raw) {
+              uint4 pk;
+              pack(fr, pk);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + (pixj * p.Co + n0 + c0)) = pk;
             }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);   // 128 arrivals release the accumulator to the MMA warp
+      mbar_arrive(&tmem_empty[set]);   // 128 arrivals release the accumulator slot to the MMA warp
+      if (et == 0) SX_TRACE(5, sup - super_begin);
       if (fuse_rgb) {
-        float* dst = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) dst[c * HWl] = rgb_acc[c];
+        for (int j = 0; j < TPS; ++j) {
+          if (j < tps) {
+            float* dst = ep.rgb_out + roff + HALO_BW * j;
+            dst[0] = rgb_acc[j][0];
+            dst[HW] = rgb_acc[j][1];
+            dst[2u * HW] = rgb_acc[j][2];
+          }
+        }
       }
-      acc ^= 1;
-      if (acc == 0) accph ^= 1;
-      b = b2; x = x2; y = y2; nz = nz2;
-      rgbp[0] = rgbp2[0]; rgbp[1] = rgbp2[1]; rgbp[2] = rgbp2[2];
+      accph ^= 1;
+      b = b2; x = x2; y = y2;
+#pragma unroll
+      for (int j = 0; j < TPS; ++j) nz[j] = nzn[j];
     }
   }
 
@@ -521,21 +756,18 @@ inline bool halo_shape_supported(int Ci, int Co, int H, int W) {
   return true;
 }
 
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS>
-int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream);
-
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B>
-int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false>(x, wk, p, stream);
-  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false>(x, wk, p, stream);
-}
-
 // x: the conv input [B,H,W,Ci] -- or, for UPS, the low-resolution tensor [B,H/2,W/2,Ci] the kernel upsamples itself
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS>
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS, int SETS, int UPS_WARPS, int TPS,
+          int MIN_CTAS>
 int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS>;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS>;
+  // a super-tile never leaves its sample or its tile row: tps divides tiles_x (both powers of two)
+  p.tps = TPS < p.tiles_x ? TPS : p.tiles_x;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  // the epilogue / producers index with 32-bit element offsets
+  const long long big = (long long)p.B * p.H * p.W * (p.Ci > p.Co ? p.Ci : p.Co);
+  if (big >= (1ll << 31)) return fail(SX_EUNSUPPORTED, "conv_tc_halo: tensor of %lld elements exceeds 32-bit indexing (split the batch)", big);
   const CUtensorMapSwizzle swz = BLOCK_K == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap ta, tb;
   {
@@ -559,7 +791,7 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS>;
+  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS, SETS, UPS_WARPS, TPS, MIN_CTAS>;
   const size_t smem = Cfg::smem_bytes(p.num_b_tiles);
   if (smem > 227 * 1024) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -572,24 +804,63 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
   if (occ_cached == 0) {
     // resident CTAs per SM, computed by hand (the occupancy API answered 1 for a kernel ncu showed could host 2:
     // it assumes the default shared-memory carve-out): 227 KB smem incl. 1 KB/CTA driver reserve, 64K registers,
-    // 512 TMEM columns.
+    // 2048 threads, 512 TMEM columns.
     SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     SX_CUDA(cudaFuncGetAttributes(&fa, kern));
     const int regs = (fa.numRegs + 7) / 8 * 8;
-    const int occ_smem = (int)((227 * 1024) / (smem + 1024));
-    const int occ_regs = 65536 / (regs * Cfg::kThreads);
-    const int occ_tmem = 512 / Cfg::kTmemCols;
-    int occ = occ_smem < occ_regs ? occ_smem : occ_regs;
-    occ = occ < occ_tmem ? occ : occ_tmem;
+    int occ = (int)((227 * 1024) / (smem + 1024));
+    occ = std::min(occ, 65536 / (regs * Cfg::kThreads));
+    occ = std::min(occ, 2048 / Cfg::kThreads);
+    occ = std::min(occ, 512 / Cfg::kTmemCols);
     occ_cached = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
   }
   int grid_x = occ_cached * num_sms();
-  if (grid_x > p.num_tiles) grid_x = p.num_tiles;
+  if (grid_x > p.num_tiles / p.tps) grid_x = p.num_tiles / p.tps;
   dim3 grid((unsigned)grid_x, (unsigned)(p.Co / BLOCK_N));
+#ifdef SX_HALO_DEBUG_KNOBS
+  // SX_HALO_TRACE=Ci_Co: clock64 stamps of the pipeline roles of CTA (0,0) for the first 64 tiles, printed for the 3rd
+  // matching launch (after warm-up)
+  static int trace_hits = 0;
+  static unsigned long long* trace_dev = nullptr;
+  bool tracing = false;
+  if (const char* tr = getenv("SX_HALO_TRACE")) {
+    char want[64];
+    snprintf(want, sizeof(want), "%d_%d_%d", p.Ci, p.Co, (int)FUSE_RGB);
+    if (!strcmp(tr, want) && ++trace_hits == 3) {
+      if (!trace_dev) cudaMalloc(&trace_dev, 8 * 64 * sizeof(unsigned long long));
+      cudaMemsetAsync(trace_dev, 0, 8 * 64 * sizeof(unsigned long long), stream);
+      p.trace = trace_dev;
+      tracing = true;
+    }
+  }
+#endif
   kern<<<grid, Cfg::kThreads, smem, stream>>>(ta, tb, p);
   SX_CHECK_LAUNCH();
+#ifdef SX_HALO_DEBUG_KNOBS
+  if (tracing) {
+    unsigned long long h[8 * 64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < 8 * 64; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+    fprintf(stderr, "HALOTRACE Ci=%d Co=%d rgb=%d tps=%d grid=%d threads=%d  (clk relative to first stamp; roles: 0 tma-issue 1 mma-slot-free 2 mma-a-ready 3 mma-issued 6 epi-at-wait 4 epi-tmem-ready 5 epi-done 7 ups-produced)\n",
+            p.Ci, p.Co, (int)FUSE_RGB, p.tps, grid_x, Cfg::kThreads);
+    for (int i = 0; i < 48; ++i) {
+      fprintf(stderr, "HALOTRACE t%02d", i);
+      for (int r = 0; r < 8; ++r) fprintf(stderr, " r%d=%lld", r, h[r * 64 + i] ? (long long)(h[r * 64 + i] - t0) : -1ll);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return SX_OK;
+}
+
+// plain (no fused upsample) configurations: ToRGB fusion is a run-time property of the epilogue descriptor
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, int SETS, int TPS, int MIN_CTAS>
+int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
+  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false, SETS, 4, TPS, MIN_CTAS>(x, wk, p, stream);
+  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false, SETS, 4, TPS, MIN_CTAS>(x, wk, p, stream);
 }
 
 inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int bk, const ConvEpilogue& ep) {
@@ -605,8 +876,17 @@ inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int 
   p.debug = dbg;
   p.kchunks = Ci / bk;
   p.num_b_tiles = 9 * p.kchunks;
+  p.tps = 1;
+  p.trace = nullptr;
   p.ep = ep;
   return p;
+}
+
+// SX_HALO_VARIANT (bitmask, tuning experiments): 1 = the 32 -> 32 layers run 3 epilogue sets x 2 tiles per slot instead of
+// 2 sets x 4 tiles
+inline int halo_variant() {
+  static const int v = getenv("SX_HALO_VARIANT") ? atoi(getenv("SX_HALO_VARIANT")) : 0;
+  return v;
 }
 
 // *handled = false (and SX_OK) when the halo kernel does not cover the shape
@@ -619,13 +899,17 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
   const bool resident = weight_bytes <= 80 * 1024;
   *handled = true;
-  if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 3, 2, true>(x, wk, p, stream);
-  if (Co == 32 && bk == 32 && resident) return launch_conv_halo_cfg<32, 32, 3, 2, true>(x, wk, p, stream);
-  if (Co == 64 && bk == 64 && resident) return launch_conv_halo_cfg<64, 64, 3, 2, true>(x, wk, p, stream);
-  // 128 -> 64 channels (147 KB of weights): still resident, with a 2-deep activation ring (197 KB of smem, 1 CTA/SM)
-  if (Co == 64 && bk == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg<64, 64, 2, 2, true>(x, wk, p, stream);
-  if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 3, 6, false>(x, wk, p, stream);
-  if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 3, 4, false>(x, wk, p, stream);
+  //                                                                    N   K  A  B  resident SETS TPS CTAs/SM
+  if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 4, 2, true, 2, 4, 1>(x, wk, p, stream);
+  if (Co == 32 && bk == 32 && resident) {
+    if (halo_variant() & 1) return launch_conv_halo_cfg<32, 32, 8, 2, true, 3, 2, 1>(x, wk, p, stream);
+    return launch_conv_halo_cfg<32, 32, 8, 2, true, 2, 4, 1>(x, wk, p, stream);
+  }
+  if (Co == 64 && bk == 64 && resident) return launch_conv_halo_cfg<64, 64, 4, 2, true, 2, 4, 1>(x, wk, p, stream);
+  // 128 -> 64 channels (147 KB of weights): still resident, with a 2-deep activation ring
+  if (Co == 64 && bk == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg<64, 64, 2, 2, true, 2, 2, 1>(x, wk, p, stream);
+  if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 4, 6, false, 2, 2, 1>(x, wk, p, stream);
+  if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 4, 4, false, 2, 2, 1>(x, wk, p, stream);
   *handled = false;
   return SX_OK;
 }
@@ -645,10 +929,11 @@ inline int launch_conv_halo_ups(const __nv_bfloat16* xlow, const __nv_bfloat16* 
   if (B == 0) return SX_OK;
   const ConvHaloParams p = make_halo_params(B, Ci, Co, H, W, 64, ep);
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
-  if (Co == 32) return launch_conv_halo_cfg2<32, 64, 2, 2, true, false, true>(xlow, wk, p, stream);
-  if (Co == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true>(xlow, wk, p, stream);
-  if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true>(xlow, wk, p, stream);
-  return launch_conv_halo_cfg2<128, 64, 3, 4, false, false, true>(xlow, wk, p, stream);
+  //                                              N   K  A  B  resident rgb   ups  SETS producer-warps TPS CTAs/SM
+  if (Co == 32) return launch_conv_halo_cfg2<32, 64, 4, 2, true, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  if (Co == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  return launch_conv_halo_cfg2<128, 64, 4, 4, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
 }
 
 // bf16 Conv2DMod dispatch: the halo-reusing persistent kernel where it applies, the per-tap kernel otherwise.
