@@ -148,16 +148,11 @@ class FusedResNetInference:
             for blk in layer:
                 if type(blk).__name__ != "BasicBlock":
                     raise TypeError("fuse_for_inference supports BasicBlock ResNets (resnet18/34)")
-                c1 = self._fold(blk.conv1, blk.bn1)
-                w2, b2, s2, p2 = self._fold(blk.conv2, blk.bn2, keep_fp32_bias=True)
-                ds = None
-                if blk.downsample is not None:
-                    # the shortcut conv's (folded-BN) bias joins conv2's bias: relu(conv2(.) + b2 + (ds(x) + bd)) -- one
-                    # elementwise pass over the shortcut less per downsampling block
-                    wd, bd, sd_, pd = self._fold(blk.downsample[0], blk.downsample[1], keep_fp32_bias=True)
-                    b2 = b2 + bd
-                    ds = (wd, None, sd_, pd)
-                self.blocks.append((c1, (w2, b2.to(dtype), s2, p2), ds))
+                # NOTE: the shortcut conv keeps its own (folded-BN) bias.  Moving it into conv2's bias would save one
+                # elementwise pass, but the un-biased shortcut can sit far from zero (BN subtracts the mean) and rounding
+                # THAT to bf16 cost up to 1.3 in the logits (measured; test_s2d_stem_matches_eager...).
+                ds = None if blk.downsample is None else self._fold(blk.downsample[0], blk.downsample[1])
+                self.blocks.append((self._fold(blk.conv1, blk.bn1), self._fold(blk.conv2, blk.bn2), ds))
         self.fc_w = model.fc.weight.detach().to(dtype)
         self.fc_b = model.fc.bias.detach().to(dtype)
         self.stem_s2d = None
@@ -204,14 +199,14 @@ class FusedResNetInference:
             x = torch.cudnn_convolution_relu(x, w, b, s, p, (1, 1), 1)
         return self._trunk(x)
 
-    def _fold(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, keep_fp32_bias: bool = False):
+    def _fold(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
         w = conv.weight.detach().float()
         scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
         b = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
         if conv.bias is not None:
             b = b + conv.bias.detach().float() * scale
         w = (w * scale[:, None, None, None]).to(self.dtype).contiguous(memory_format=torch.channels_last)
-        return w, (b if keep_fp32_bias else b.to(self.dtype)), tuple(conv.stride), tuple(conv.padding)
+        return w, b.to(self.dtype), tuple(conv.stride), tuple(conv.padding)
 
     def _trunk(self, x: torch.Tensor) -> torch.Tensor:
         x = self._pool(x)

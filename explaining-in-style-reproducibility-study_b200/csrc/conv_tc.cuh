@@ -43,13 +43,35 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// try_wait with a suspend-time hint: the thread sleeps IN HARDWARE until the phase completes or ~hint_ns elapse.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+// ncu (profiles/README.md): with a bare try_wait + clock64 watchdog in the loop, the ~25 waiting warps of the persistent
+// kernels polled ~800 times per tile and burnt 50-70 % of the SM's issue slots (ISETP / BRA / IADD3 / CS2R / YIELD were
+// the five most executed opcodes), starving the MMA-issuing and epilogue warps.  Now: one plain try_wait (the common,
+// already-complete case), then hardware-suspended waits of up to 20 us each; the watchdog counts those (~2 s in total)
+// (~2 s of wall clock, sampled every 64 wake-ups) instead of reading the clock per poll.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int which) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kWatchdogCycles) {
-      printf("stylex_b200 conv_tc: barrier %d timed out (block %d,%d thread %d)\n", which, blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++spins & 63u) == 0) {   // the clock is read once per 64 wake-ups, not per poll
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWatchdogCycles) {
+        printf("stylex_b200 conv_tc: barrier %d timed out (block %d,%d thread %d)\n", which, blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+      }
     }
   }
 }

@@ -57,20 +57,21 @@ constexpr int halo_pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 
 // thread drains pixel r of all TPS tiles in one pass, so each per-channel table value it fetches from shared memory
 // (a broadcast LDS: 128 threads read the same word) serves TPS pixels.  ncu: with TPS = 1 those table loads were 55-60 %
 // of the shared-memory wavefronts of the narrow layers, whose L1/shared data pipe ran at 80-85 % -- the actual bound.
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS, int SETS, int UPS_WARPS, int TPS>
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS, int SETS, int UPS_WARPS, int TPS, int NMMA>
 struct HaloCfg {
   static_assert(SETS >= 2 && SETS <= 4, "2..4 accumulator slots / epilogue sets");
-  static_assert(TPS == 2 || TPS == 4, "tiles per accumulator slot (even: the two MMA warps take alternate tiles)");
-  // The activation ring (and the weight ring, when weights stream) is split in two halves, one per MMA warp: even tiles
-  // go through half 0, odd tiles through half 1.  An mbarrier parity wait can only tell adjacent phases apart, so every
-  // ring needs a single in-order consumer.
-  static_assert(A_STAGES % 2 == 0 && (RESIDENT_B || B_STAGES % 2 == 0), "rings are split between the two MMA warps");
-  static constexpr int kAHalf = A_STAGES / 2, kBHalf = B_STAGES / 2;
+  static_assert(TPS == 1 || TPS == 2, "tiles per accumulator slot (W >= 16 guarantees two tiles per tile row)");
+  static_assert(NMMA == 1 || NMMA == 2, "one or two MMA-issuing warps");
+  // With two MMA warps, warp m issues super-tiles m, m + 2, ...; the activation ring (and the weight ring, when weights
+  // stream) is split into one part per warp, filled by the producers according to the super-tile's parity.  An mbarrier
+  // parity wait can only tell adjacent phases apart, so every ring needs a single in-order consumer.
+  static_assert(A_STAGES % NMMA == 0 && (RESIDENT_B || B_STAGES % NMMA == 0), "rings are split between the MMA warps");
+  static constexpr int kAHalf = A_STAGES / NMMA, kBHalf = B_STAGES / NMMA;
   static_assert(!UPS || UPS_WARPS == 4 || UPS_WARPS == 8, "4 (8 channels per thread) or 8 (4 channels per thread) producer warps");
   static constexpr int kRowBytes = BLOCK_K * 2;
   static constexpr int kEpiThreads = 128 * SETS;
   static constexpr int kUpsThreads = UPS ? 32 * UPS_WARPS : 0;
-  static constexpr int kFrontThreads = 128;   // warp 0 TMA, warps 1-2 MMA issuers, warp 3 idle (keeps the sets 4-aligned)
+  static constexpr int kFrontThreads = 128;   // warp 0 TMA, warps 1..NMMA MMA issuers, the rest of the first four idle (sets stay 4-aligned)
   static constexpr int kThreads = kFrontThreads + kEpiThreads + kUpsThreads;
   static constexpr int kSrcBytes = UPS_SRC_W * UPS_SRC_H * kRowBytes;   // one source box (7680 B at BLOCK_K = 64)
   static constexpr int kSrcRegion = UPS ? UPS_S_STAGES * kSrcBytes : 0;
@@ -165,10 +166,10 @@ __device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
 }
 
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS, int SETS, int UPS_WARPS,
-          int TPS, int MIN_CTAS>
-__global__ void __launch_bounds__(HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS>::kThreads, MIN_CTAS)
+          int TPS, int NMMA>
+__global__ void __launch_bounds__(HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA>::kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvHaloParams p) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS>;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA>;
   static_assert(!UPS || BLOCK_K == 64, "the fused-upsample producer writes the SWIZZLE_128B layout");
   extern __shared__ uint8_t smem_raw[];
   // offset arithmetic on the __shared__ array (not an integer round trip) keeps the shared address space known to the
@@ -198,11 +199,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // the per-sample epilogue tables -- changes once per several hundred tiles instead of every other tile, and
   // consecutive tiles share halo columns in L2.
   // The unit of the walk is the super-tile (tps tiles: one accumulator slot).
-  const int tps = p.tps;
+  constexpr int tps = TPS;   // compile-time: the launcher guarantees tiles_x >= TPS
   const int num_super = p.num_tiles / tps;
   const int super_begin = (int)((long long)blockIdx.x * num_super / gridDim.x);
   const int super_end = (int)((long long)(blockIdx.x + 1) * num_super / gridDim.x);
   const int tile_begin = super_begin * tps, tile_end = super_end * tps;
+  constexpr int tps_shift = TPS == 2 ? 1 : 0;
 #ifdef SX_HALO_DEBUG_KNOBS   // bottleneck experiments only (profiles/README.md); never in the shipped library
   const int dbg = p.debug;
 #else
@@ -226,7 +228,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], UPS ? Cfg::kUpsThreads : 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < SETS; ++s) { mbar_init(&tmem_full[s], 2); mbar_init(&tmem_empty[s], 128); }   // full: one commit per MMA warp
+    for (int s = 0; s < SETS; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
     if (UPS) for (int s = 0; s < UPS_S_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], Cfg::kUpsThreads); }
     fence_barrier_init();
   } else if (warp_id == 1) {
@@ -258,7 +260,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int tr = tile - (b << p.tpb_shift);
         const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
         const int x0 = tx * HALO_BW, y0 = ty * HALO_BH;
-        const int rg = (tile - tile_begin) & 1;
+        const int rg = NMMA == 2 ? (((tile - tile_begin) >> tps_shift) & 1) : 0;
         int as = rg ? as2[1] : as2[0], bs = rg ? bs2[1] : bs2[0];
         uint32_t aph = rg ? aph2[1] : aph2[0], bph = rg ? bph2[1] : bph2[0];
         for (int chunk = 0; chunk < p.kchunks; ++chunk) {
@@ -306,14 +308,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         else { as2[0] = as; aph2[0] = aph; bs2[0] = bs; bph2[0] = bph; }
       }
     }
-  } else if (warp_id == 1 || warp_id == 2) {
-    // ===================== MMA issuers (two warps; warp-uniform control flow, one elected lane issues) =====================
-    // Pipeline traces (profiles/README.md) showed ONE issuing warp pacing every layer this kernel serves: tcgen05.mma issue
-    // blocks while the (short) MMA queue is full, so the warp spends the tile's whole MMA time inside the issue loop and
-    // only then runs its per-tile bookkeeping (barrier waits, fences, descriptors: 500-1000 cycles of dependent scalar
-    // code) with the tensor pipe idle -- ~38 % of the cadence.  Two warps take alternate tiles: while one is blocked
-    // issuing, the other does its bookkeeping, and the queue never drains.  Ring positions are functions of the tile
-    // index, so neither warp needs the other's state; both commit to the slot's tmem_full barrier (count 2).
+  } else if (warp_id >= 1 && warp_id <= NMMA) {
+    // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) =====================
+    // Pipeline traces (profiles/README.md) showed ONE issuing warp pacing the narrow layers: tcgen05.mma issue blocks while
+    // the (short) MMA queue is full, so the warp spends the tile's whole MMA time inside the issue loop and only then
+    // runs its per-tile bookkeeping (barrier waits, fences, descriptors: 500-1000 cycles of dependent scalar code) with
+    // the tensor pipe idle.  With NMMA = 2, warp m issues super-tiles m, m + 2, ... from its own part of the rings: while
+    // one warp is blocked issuing, the other does its bookkeeping.
     {
       const int mw = warp_id - 1;
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
@@ -322,7 +323,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&b_full[0], 0, 12);
         tc_fence_after();
       }
-      const uint32_t a_base0 = smem_u32(smem_a) + (uint32_t)(mw * Cfg::kAHalf * Cfg::kABytes);   // this warp's half of the A ring
+      const uint32_t a_base0 = smem_u32(smem_a) + (uint32_t)(mw * Cfg::kAHalf * Cfg::kABytes);   // this warp's part of the A ring
       const uint32_t b_base0 = smem_u32(smem_b) + (RESIDENT_B ? 0u : (uint32_t)(mw * Cfg::kBHalf * Cfg::kBBytes));
       uint64_t* my_a_full = a_full + mw * Cfg::kAHalf;
       uint64_t* my_a_empty = a_empty + mw * Cfg::kAHalf;
@@ -330,70 +331,68 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint64_t* my_b_empty = b_empty + (RESIDENT_B ? 0 : mw * Cfg::kBHalf);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      const int tps_shift = tps == 4 ? 2 : 1;        // tps is 2 or 4
-      for (int tile = tile_begin + mw; tile < tile_end; tile += 2) {
-        const int ti = tile - tile_begin;
-        const int si = ti >> tps_shift, sub = ti - (si << tps_shift);
+      const int nsuper = super_end - super_begin;
+      for (int si = mw; si < nsuper; si += NMMA) {
         const int acc = si % SETS;
         const uint32_t accph = (uint32_t)(si / SETS) & 1u;
-        if (sub < 2) {   // this warp's first tile of the super-tile
-          mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // this slot's epilogue set has drained the accumulators
-          tc_fence_after();
-        }
-        if (lane == 0) SX_TRACE(1, ti);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kSlotCols + sub * BLOCK_N);
-        for (int chunk = 0; chunk < p.kchunks; ++chunk) {
-          mbar_wait(&my_a_full[as], aph, 14);
-          tc_fence_after();
-          if (lane == 0 && chunk == 0) SX_TRACE(2, ti);
-          // descriptors of tap 0; every other tap / k step is this plus a compile-time constant (fully unrolled)
-          const uint64_t da0 = make_smem_desc_sbo<BLOCK_K>(a_base0 + (uint32_t)(as * Cfg::kABytes), sbo);
-          const uint64_t db_res = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(chunk * 9 * Cfg::kBBytes));
-          if (RESIDENT_B) {
-            // weights resident: nothing to wait for inside the chunk -- one election, 9 x BLOCK_K/16 back-to-back MMAs
-            if (elect_one()) {
-              if (!(dbg & 2)) {
-#pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                  const int ky = tap / 3, kx = tap - ky * 3;
-                  const uint64_t da = da0 + (uint64_t)(((ky * HALO_W + kx) * Cfg::kRowBytes) >> 4);
-                  const uint64_t db = db_res + (uint64_t)((tap * Cfg::kBBytes) >> 4);
-#pragma unroll
-                  for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                    umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
-                }
-              }
-            }
-            __syncwarp();
-          } else {
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&my_b_full[bs], bph, 15);
-              tc_fence_after();
-              const uint64_t db = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(bs * Cfg::kBBytes));
-              const int ky = tap / 3, kx = tap - ky * 3;
-              const uint64_t da = da0 + (uint64_t)(((ky * HALO_W + kx) * Cfg::kRowBytes) >> 4);
+        mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // this slot's epilogue set has drained the accumulators
+        tc_fence_after();
+        for (int sub = 0; sub < tps; ++sub) {
+          const int ti = (si << tps_shift) + sub;
+          (void)ti;
+          if (lane == 0) SX_TRACE(1, ti);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kSlotCols + sub * BLOCK_N);
+          for (int chunk = 0; chunk < p.kchunks; ++chunk) {
+            mbar_wait(&my_a_full[as], aph, 14);
+            tc_fence_after();
+            if (lane == 0 && chunk == 0) SX_TRACE(2, ti);
+            // descriptors of tap 0; every other tap / k step is this plus a compile-time constant (fully unrolled)
+            const uint64_t da0 = make_smem_desc_sbo<BLOCK_K>(a_base0 + (uint32_t)(as * Cfg::kABytes), sbo);
+            const uint64_t db_res = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(chunk * 9 * Cfg::kBBytes));
+            if (RESIDENT_B) {
+              // weights resident: nothing to wait for inside the chunk -- one election, 9 x BLOCK_K/16 back-to-back MMAs
               if (elect_one()) {
                 if (!(dbg & 2)) {
 #pragma unroll
-                  for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                    umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                  for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const uint64_t da = da0 + (uint64_t)(((ky * HALO_W + kx) * Cfg::kRowBytes) >> 4);
+                    const uint64_t db = db_res + (uint64_t)((tap * Cfg::kBBytes) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                      umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                  }
                 }
-                umma_commit(&my_b_empty[bs]);
+                umma_commit(&my_a_empty[as]);
               }
               __syncwarp();
-              if (++bs == Cfg::kBHalf) { bs = 0; bph ^= 1; }
+            } else {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(&my_b_full[bs], bph, 15);
+                tc_fence_after();
+                const uint64_t db = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(bs * Cfg::kBBytes));
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint64_t da = da0 + (uint64_t)(((ky * HALO_W + kx) * Cfg::kRowBytes) >> 4);
+                if (elect_one()) {
+                  if (!(dbg & 2)) {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                      umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (chunk | tap | k) != 0 ? 1u : 0u);
+                  }
+                  umma_commit(&my_b_empty[bs]);
+                  if (tap == 8) umma_commit(&my_a_empty[as]);
+                }
+                __syncwarp();
+                if (++bs == Cfg::kBHalf) { bs = 0; bph ^= 1; }
+              }
             }
+            if (++as == Cfg::kAHalf) { as = 0; aph ^= 1; }
           }
-          if (elect_one()) umma_commit(&my_a_empty[as]);
-          __syncwarp();
-          if (++as == Cfg::kAHalf) { as = 0; aph ^= 1; }
+          if (lane == 0) SX_TRACE(3, ti);
         }
-        if (lane == 0) SX_TRACE(3, ti);
-        if (sub + 2 >= tps) {   // this warp's last tile of the super-tile: its half of the hand-over to the epilogue set
-          if (elect_one()) umma_commit(&tmem_full[acc]);
-          __syncwarp();
-        }
+        if (elect_one()) umma_commit(&tmem_full[acc]);   // hand the super-tile to its epilogue set
+        __syncwarp();
       }
     }
   } else if (UPS && warp_id >= 4 + 4 * SETS) {
@@ -420,7 +419,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int b = tile >> p.tpb_shift;
       const int tr = tile - (b << p.tpb_shift);
       const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
-      const int rg = (tile - tile_begin) & 1;
+      const int rg = NMMA == 2 ? (((tile - tile_begin) >> tps_shift) & 1) : 0;
       int as = rg ? as2[1] : as2[0];
       uint32_t aph = rg ? aph2[1] : aph2[0];
       const bool left = tx == 0, right = tx == p.tiles_x - 1, top = ty == 0, bottom = ty == p.tiles_y - 1;
@@ -609,18 +608,27 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out) + ((size_t)pix * (uint32_t)p.Co + (uint32_t)n0);
         __nv_bfloat16* rawp = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + ((size_t)pix * (uint32_t)p.Co + (uint32_t)n0);
         const uint32_t jstride = (uint32_t)(HALO_BW * p.Co);   // elements between this thread's pixels of consecutive tiles
-        constexpr int CW = TPS == 4 ? 8 : 16;   // columns per pass: bounds the live registers (v, om, orw scale with TPS * CW)
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
-          uint32_t v[TPS][CW];
+        // CW columns per pass, double-buffered: the TMEM loads of pass k + 1 are in flight during the math of pass k.
+        // The register budget (threads per CTA) picks the width.
+        constexpr int CW = Cfg::kThreads <= 384 ? 16 : 8;
+        constexpr int NPASS = BLOCK_N / CW;
+        uint32_t v[2][TPS][CW];
+        auto issue_loads = [&](int pass, uint32_t (*dst)[CW]) {
 #pragma unroll
           for (int j = 0; j < TPS; ++j) {
-            if (j < tps) {
-              if constexpr (CW == 16) tmem_ld16(tbase + (uint32_t)(j * BLOCK_N + c0), v[j]);
-              else tmem_ld8(tbase + (uint32_t)(j * BLOCK_N + c0), v[j]);
-            }
+            if constexpr (CW == 16) tmem_ld16(tbase + (uint32_t)(j * BLOCK_N + pass * CW), dst[j]);
+            else tmem_ld8(tbase + (uint32_t)(j * BLOCK_N + pass * CW), dst[j]);
           }
+        };
+        issue_loads(0, v[0]);
+        // fully unrolled: the buffer index must be a compile-time constant (a run-time index, or passing the buffers
+        // through a helper, sends v[] to local memory -- measured: 1.6x slower)
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+          const int c0 = pass * CW;
           tmem_ld_wait();
+          if (pass + 1 < NPASS) issue_loads(pass + 1, v[(pass + 1) & 1]);
+          uint32_t (*vv)[CW] = v[pass & 1];
           uint32_t om[TPS][CW / 2], orw[TPS][CW / 2];
 #pragma unroll
           for (int g = 0; g < CW / 4; ++g) {
@@ -641,10 +649,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int j = 0; j < TPS; ++j) {
               if (j < tps) {
                 if (has_out) {
-                  if (has_raw) epi_group4<fuse_rgb, true, true>(v[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
-                  else epi_group4<fuse_rgb, true, false>(v[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
+                  if (has_raw) epi_group4<fuse_rgb, true, true>(vv[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
+                  else epi_group4<fuse_rgb, true, false>(vv[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
                 } else {
-                  epi_group4<fuse_rgb, false, false>(v[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
+                  epi_group4<fuse_rgb, false, false>(vv[j] + 4 * g, t, pk2(nz[j], nz[j]), om[j] + 2 * g, orw[j] + 2 * g, racc[j]);
                 }
               }
             }
@@ -758,11 +766,12 @@ inline bool halo_shape_supported(int Ci, int Co, int H, int W) {
 
 // x: the conv input [B,H,W,Ci] -- or, for UPS, the low-resolution tensor [B,H/2,W/2,Ci] the kernel upsamples itself
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS, int SETS, int UPS_WARPS, int TPS,
-          int MIN_CTAS>
+          int NMMA>
 int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS>;
-  // a super-tile never leaves its sample or its tile row: tps divides tiles_x (both powers of two)
-  p.tps = TPS < p.tiles_x ? TPS : p.tiles_x;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA>;
+  // a super-tile never leaves its sample or its tile row: TPS divides tiles_x (a power of two >= 2, since W >= 16)
+  if (p.tiles_x % TPS != 0) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %d tiles per row is not a multiple of %d", p.tiles_x, TPS);
+  p.tps = TPS;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SX_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   // the epilogue / producers index with 32-bit element offsets
@@ -791,7 +800,7 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS, SETS, UPS_WARPS, TPS, MIN_CTAS>;
+  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS, SETS, UPS_WARPS, TPS, NMMA>;
   const size_t smem = Cfg::smem_bytes(p.num_b_tiles);
   if (smem > 227 * 1024) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -813,7 +822,8 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
     occ = std::min(occ, 65536 / (regs * Cfg::kThreads));
     occ = std::min(occ, 2048 / Cfg::kThreads);
     occ = std::min(occ, 512 / Cfg::kTmemCols);
-    occ_cached = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
+    occ_cached = 1;   // every configuration is sized for one CTA per SM (__launch_bounds__(threads, 1))
+    (void)occ;
   }
   int grid_x = occ_cached * num_sms();
   if (grid_x > p.num_tiles / p.tps) grid_x = p.num_tiles / p.tps;
@@ -857,10 +867,10 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
 }
 
 // plain (no fused upsample) configurations: ToRGB fusion is a run-time property of the epilogue descriptor
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, int SETS, int TPS, int MIN_CTAS>
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, int SETS, int TPS, int NMMA>
 int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false, SETS, 4, TPS, MIN_CTAS>(x, wk, p, stream);
-  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false, SETS, 4, TPS, MIN_CTAS>(x, wk, p, stream);
+  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false, SETS, 4, TPS, NMMA>(x, wk, p, stream);
+  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false, SETS, 4, TPS, NMMA>(x, wk, p, stream);
 }
 
 inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int bk, const ConvEpilogue& ep) {
@@ -882,8 +892,9 @@ inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int 
   return p;
 }
 
-// SX_HALO_VARIANT (bitmask, tuning experiments): 1 = the 32 -> 32 layers run 3 epilogue sets x 2 tiles per slot instead of
-// 2 sets x 4 tiles
+// SX_HALO_VARIANT (bitmask, tuning experiments): 1 = the 32 -> 32 layers run 2 epilogue sets (wide passes) instead of 4;
+// 2 = the 64 -> 64 layers run 2 sets x 2 tiles with two MMA warps instead of 4 sets x 1 tile with one;
+// 4 = the fused-upsample 128 -> 64 layer runs 2 tiles per slot with two MMA warps
 inline int halo_variant() {
   static const int v = getenv("SX_HALO_VARIANT") ? atoi(getenv("SX_HALO_VARIANT")) : 0;
   return v;
@@ -899,17 +910,20 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
   const bool resident = weight_bytes <= 80 * 1024;
   *handled = true;
-  //                                                                    N   K  A  B  resident SETS TPS CTAs/SM
-  if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 4, 2, true, 2, 4, 1>(x, wk, p, stream);
+  //                                                                    N   K  A  B  resident SETS TPS MMA-warps
+  if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 4, 2, true, 4, 2, 2>(x, wk, p, stream);
   if (Co == 32 && bk == 32 && resident) {
-    if (halo_variant() & 1) return launch_conv_halo_cfg<32, 32, 8, 2, true, 3, 2, 1>(x, wk, p, stream);
-    return launch_conv_halo_cfg<32, 32, 8, 2, true, 2, 4, 1>(x, wk, p, stream);
+    if (halo_variant() & 1) return launch_conv_halo_cfg<32, 32, 8, 2, true, 2, 2, 2>(x, wk, p, stream);
+    return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2>(x, wk, p, stream);
   }
-  if (Co == 64 && bk == 64 && resident) return launch_conv_halo_cfg<64, 64, 4, 2, true, 2, 4, 1>(x, wk, p, stream);
+  if (Co == 64 && bk == 64 && resident) {
+    if (halo_variant() & 2) return launch_conv_halo_cfg<64, 64, 4, 2, true, 2, 2, 2>(x, wk, p, stream);
+    return launch_conv_halo_cfg<64, 64, 4, 2, true, 4, 1, 1>(x, wk, p, stream);
+  }
   // 128 -> 64 channels (147 KB of weights): still resident, with a 2-deep activation ring
-  if (Co == 64 && bk == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg<64, 64, 2, 2, true, 2, 2, 1>(x, wk, p, stream);
-  if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 4, 6, false, 2, 2, 1>(x, wk, p, stream);
-  if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 4, 4, false, 2, 2, 1>(x, wk, p, stream);
+  if (Co == 64 && bk == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg<64, 64, 2, 2, true, 4, 1, 1>(x, wk, p, stream);
+  if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 3, 6, false, 4, 1, 1>(x, wk, p, stream);
+  if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 3, 4, false, 2, 2, 1>(x, wk, p, stream);
   *handled = false;
   return SX_OK;
 }
@@ -929,11 +943,14 @@ inline int launch_conv_halo_ups(const __nv_bfloat16* xlow, const __nv_bfloat16* 
   if (B == 0) return SX_OK;
   const ConvHaloParams p = make_halo_params(B, Ci, Co, H, W, 64, ep);
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
-  //                                              N   K  A  B  resident rgb   ups  SETS producer-warps TPS CTAs/SM
-  if (Co == 32) return launch_conv_halo_cfg2<32, 64, 4, 2, true, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
-  if (Co == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
-  if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
-  return launch_conv_halo_cfg2<128, 64, 4, 4, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  //                                              N   K  A  B  resident rgb   ups  SETS producer-warps TPS MMA-warps
+  if (Co == 32) return launch_conv_halo_cfg2<32, 64, 4, 2, true, false, true, 4, 8, 2, 2>(xlow, wk, p, stream);
+  if (Co == 64 && weight_bytes <= 150 * 1024) {
+    if (halo_variant() & 4) return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 4, 8, 2, 2>(xlow, wk, p, stream);
+    return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 4, 8, 1, 1>(xlow, wk, p, stream);
+  }
+  if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true, 4, 8, 1, 1>(xlow, wk, p, stream);
+  return launch_conv_halo_cfg2<128, 64, 3, 4, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
 }
 
 // bf16 Conv2DMod dispatch: the halo-reusing persistent kernel where it applies, the per-tap kernel otherwise.
