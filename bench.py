@@ -59,7 +59,7 @@ def parse():
                     help="classifier input pipeline: one native kernel or torchvision resize + Normalize")
     ap.add_argument("--latents-per-step", type=int, default=1)
     ap.add_argument("--pool", type=int, default=16, help="latents per rank prepared up front (minima/maxima pool)")
-    ap.add_argument("--max-batch", type=int, default=128)
+    ap.add_argument("--max-batch", type=int, default=256)
     ap.add_argument("--cpu-sample-coords", type=int, default=160, help="style coordinates in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -455,7 +455,7 @@ def run_ours(args):
                                f"AttFind sweep, {lps} latent(s)/rank/step x {S} coords x 2 directions",
                    "coord_evals_per_step": int(2 * S * lps * world), "max_batch": args.max_batch,
                    "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)", "classifier_mode": clf_mode, "classifier_preprocess": pre_mode,
-                   "prefix_reuse": True, "l2": "inputs larger than L2: every 128-eval batch streams >2 GB of activations (L2 = 126 MB)",
+                   "prefix_reuse": True, "l2": f"inputs larger than L2: every {args.max_batch}-eval batch streams >{args.max_batch * 16.8e6 / 1e9:.1f} GB of activations (L2 = 126 MB)",
                    "pool_latents": pool_n, "parallelism": f"latent-sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roofline, "cpu_baseline": cpu,
         "conv_flops_per_full_image": conv_flops_per_image(plan.pairs),

@@ -1,7 +1,8 @@
 """B200-native AttFind hot path of StylEx (drop-in for the reference's Python surface).
 
 See DESIGN.md.  Host-side mirror of the reference interface: ``modules`` (Generator, GeneratorBlock,
-RGBBlock, Conv2DMod, Blur), ``attfind`` (attfind_extraction, find_significant_styles, ...), ``classifiers``
+RGBBlock, Conv2DMod, Blur), ``attfind`` (attfind_extraction, find_significant_styles, ...), ``counterfactual``
+(generate_change_image_given_dlatent, generate_images_given_dlatent, visualize_style), ``classifiers``
 (ResNet / MobileNet wrappers, PyTorch), ``dist`` (latent sharding + the one all-gather).  The CUDA kernels and
 the C-ABI library live under ``csrc`` (declared in ``include/stylex_b200.h``, bound in ``_native``).
 """
@@ -12,5 +13,7 @@ from .modules import (Blur, Conv2DMod, Generator, GeneratorBlock, GeneratorPlan,
 from .classifiers import MobileNet, ResNet, make_classifier  # noqa: F401
 from .attfind import (attfind_extraction, attfind_select, attfind_sweep, find_significant_styles,  # noqa: F401
                       get_min_max_style_vectors, sindex_to_block_idx_and_index)
+from .counterfactual import (draw_on_image, generate_change_image_given_dlatent, generate_images_given_dlatent,  # noqa: F401
+                             render_counterfactuals, visualize_style)
 
 __version__ = "0.1.0"

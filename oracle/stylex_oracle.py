@@ -281,3 +281,51 @@ def attfind_select(style_change_effect: np.ndarray, base_probs: np.ndarray, num_
     order = np.argsort(scores)[::-1]                                         # NB:811
     merged = [joined[i] for i in order]
     return picks, merged, [float(scores[i]) for i in order]
+
+
+# --------------------------------------------------------------------------------------
+# L5 counterfactual rendering (NB cells 17-19) -- the step after the selection
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def generate_change_image_given_dlatent(params: Dict[str, Tensor], classify: Callable[[Tensor], Tensor], dlatent: Tensor,
+                                        class_index: int, sindex: int, s_style_min: float, s_style_max: float,
+                                        style_direction_index: int, shift_size: float, noise: Tensor):
+    """NB cell 17 (``generate_change_image_given_dlatent``), functional form of its bias patch.
+
+    dlatent [B,514].  Style coordinate ``sindex`` moves by ``(target - coord) * shift_size`` with target = the
+    coordinate's minimum (direction 0) or maximum (direction 1); returns (images [B,3,S,S], softmax probability of
+    ``class_index`` per image [B]).  The notebook only ever passes B = 1 and returns element 0 of the probabilities.
+    """
+    pairs = generator_layout(params)
+    S = sum(ci + co for ci, co in pairs)
+    w = styles_def_to_tensor([(dlatent, len(pairs))])
+    _, coords = generator_forward(params, w, noise, get_style_coords=True)
+    target = s_style_min if style_direction_index == 0 else s_style_max
+    shift = torch.zeros(dlatent.shape[0], S)
+    shift[:, sindex] = (float(target) - coords[:, sindex]) * shift_size
+    images = generator_forward(params, w, noise, coord_shift=shift)
+    probs = torch.softmax(classify(images), dim=1)[:, class_index]
+    return images, probs
+
+
+def draw_on_image(image: np.ndarray) -> np.ndarray:
+    """NB cell 18 with its text drawing commented out, as in the reference: CHW float -> HWC uint8 of clip(x, 0, 1) * 255."""
+    image = np.clip(np.transpose(image, (1, 2, 0)), 0, 1)
+    return (image * 255).astype(np.uint8)
+
+
+@torch.no_grad()
+def generate_images_given_dlatent(params, classify, dlatent: Tensor, class_index: int, sindex: int, s_style_min: float,
+                                  s_style_max: float, style_direction_index: int, noise: Tensor, shift_size: float = 2):
+    """NB cell 19 (``draw_results_on_image=True`` branch): (panel uint8 [res, 2*res, 3], change_prob, base_prob)."""
+    pairs = generator_layout(params)
+    w = styles_def_to_tensor([(dlatent, len(pairs))])
+    base = generator_forward(params, w, noise)
+    base_prob = float(torch.softmax(classify(base), dim=1)[0, class_index])
+    change, prob = generate_change_image_given_dlatent(params, classify, dlatent, class_index, sindex, s_style_min,
+                                                       s_style_max, style_direction_index, shift_size, noise)
+    res = base.shape[-1]
+    panel = np.zeros((res, 2 * res, 3), np.uint8)
+    panel[:, :res] = draw_on_image(base[0].numpy())
+    panel[:, res:] = draw_on_image(change[0].numpy())
+    return panel, float(prob[0]), base_prob

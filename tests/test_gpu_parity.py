@@ -496,6 +496,48 @@ def test_native_maxpool_is_bit_identical(dev, dtype, shape):
     assert bool(torch.isnan(got).any()) == bool(torch.isnan(ref).any())
 
 
+@pytest.mark.parametrize("kind", ["mobilenet", "resnet"])
+def test_counterfactual_rendering_vs_verbatim_notebook_golden(dev, golden, kind):
+    """NB cells 17-20 through the native generator plan vs the golden vectors of the executed reference."""
+    z = golden("attfind_small.npz")
+    c = golden("counterfactual_small.npz")
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    sd = state_from_npz(z, "G.")
+    G = g_module(sd, size, cap, dev)
+    G.precision = "fp32"
+    clf = sx.make_classifier(kind, tiny_cnn_from(z, f"{kind}.clf.").to(dev), size)
+    latents = torch.from_numpy(z[f"{kind}.latents"]).to(dev)
+    noise = torch.from_numpy(z["noise"]).to(dev)
+    smin, smax = z[f"{kind}.minima"][0], z[f"{kind}.maxima"][0]
+    for i, (n, sindex, d, cls, shift) in enumerate(c[f"{kind}.cases"]):
+        n, sindex, d, cls = int(n), int(sindex), int(d), int(cls)
+        img, prob = sx.generate_change_image_given_dlatent([(latents[n:n + 1], G.num_layers)], G, clf, cls, sindex,
+                                                           smin[sindex], smax[sindex], d, float(shift), 2, noise, 0)
+        assert float((img[0].cpu() - torch.from_numpy(c[f"{kind}.images"][i])).abs().max()) <= FP32_TOL
+        assert abs(float(prob) - c[f"{kind}.change_prob"][i]) <= 1e-4
+        panel, cp, bp = sx.generate_images_given_dlatent(latents[n:n + 1].cpu().numpy(), G, clf, cls, sindex, smin[sindex],
+                                                         smax[sindex], d, None, noise, shift_size=float(shift),
+                                                         resolution=size, gen_num_layers=G.num_layers)
+        assert abs(bp - c[f"{kind}.base_prob"][i]) <= 1e-4 and abs(cp - c[f"{kind}.change_prob"][i]) <= 1e-4
+        diff = np.abs(panel.astype(np.int32) - c[f"{kind}.panels"][i].astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 0.02
+    # batched primitive == one-by-one; visualize_style keeps the notebook's selection rules
+    sindex, d = int(c[f"{kind}.cases"][0][1]), int(c[f"{kind}.cases"][0][2])
+    imgs, probs = sx.render_counterfactuals(G, clf, latents, sindex, smin[sindex], smax[sindex], d, 2.0, noise, 1)
+    one, p1 = sx.render_counterfactuals(G, clf, latents[2:3], sindex, smin[sindex], smax[sindex], d, 2.0, noise, 1)
+    assert torch.equal(imgs[2:3], one) and float((probs[2:3] - p1).abs().max()) <= 1e-6
+    eff = np.zeros((latents.shape[0], 2, G.num_style_coords, 2), np.float32)
+    eff[:, d, sindex, 1] = 1.0
+    grid = sx.visualize_style(G, clf, latents.cpu().numpy(), eff, smin, smax, sindex, d, max_images=4, shift_size=2.0,
+                              noise=noise, class_index=1, effect_threshold=0.0, seed=3)
+    assert grid.shape == (4 * size, 2 * size, 3) and grid.dtype == np.uint8
+    none = sx.visualize_style(G, clf, latents.cpu().numpy(), eff, smin, smax, sindex, d, max_images=4, shift_size=2.0,
+                              noise=noise, class_index=1, effect_threshold=5.0, seed=3)
+    assert none.size == 0
+    with pytest.raises(IndexError):
+        sx.render_counterfactuals(G, clf, latents, G.num_style_coords, 0.0, 1.0, 0, 1.0, noise)
+
+
 def test_edge_cases_empty_and_ragged(dev):
     """empty batches are no-ops, a single latent works (min == max: every shift is 0), odd batch sizes and coordinate
     subsets that straddle conv boundaries are handled."""

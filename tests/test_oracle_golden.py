@@ -87,6 +87,29 @@ def test_find_significant_styles_cases(golden):
             assert got == [tuple(p) for p in z[f"{name}.picks{c}"]], (name, c)
 
 
+@pytest.mark.parametrize("kind", ["mobilenet", "resnet"])
+def test_counterfactual_rendering_matches_verbatim_notebook(golden, kind):
+    """oracle restatement of NB cells 17-19 vs the executed reference (tests/golden/make_golden.py::counterfactual_small)."""
+    z = golden("attfind_small.npz")
+    c = golden("counterfactual_small.npz")
+    sd = state_from_npz(z, "G.")
+    clf = classifiers.make_classifier(kind, tiny_cnn_from(z, f"{kind}.clf."), int(z["image_size"]))
+    latents = torch.from_numpy(z[f"{kind}.latents"])
+    noise = torch.from_numpy(z["noise"])
+    smin, smax = z[f"{kind}.minima"][0], z[f"{kind}.maxima"][0]
+    for i, (n, sindex, d, cls, shift) in enumerate(c[f"{kind}.cases"]):
+        n, sindex, d, cls = int(n), int(sindex), int(d), int(cls)
+        img, prob = O.generate_change_image_given_dlatent(sd, clf.classify_images, latents[n:n + 1], cls, sindex,
+                                                          smin[sindex], smax[sindex], d, float(shift), noise)
+        assert np.abs(img[0].numpy() - c[f"{kind}.images"][i]).max() <= 5e-6
+        assert abs(float(prob[0]) - c[f"{kind}.change_prob"][i]) <= 1e-5
+        panel, cp, bp = O.generate_images_given_dlatent(sd, clf.classify_images, latents[n:n + 1], cls, sindex, smin[sindex],
+                                                        smax[sindex], d, noise, shift_size=float(shift))
+        assert abs(bp - c[f"{kind}.base_prob"][i]) <= 1e-5 and abs(cp - c[f"{kind}.change_prob"][i]) <= 1e-5
+        diff = np.abs(panel.astype(np.int32) - c[f"{kind}.panels"][i].astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 0.01      # uint8 truncation at an integer boundary
+
+
 def test_sindex_mapping():
     pairs = synthetic.generator_pairs(64)
     assert O.sindex_to_block_idx_and_index(pairs, 0) == (0, 0)
