@@ -10,6 +10,10 @@
 //   Wk = weights packed [Co][tap*Ci + ci] (K-major), shared by the whole batch (style lives in A / epilogue)
 // One K block = BLOCK_K channels of one tap.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator +
 // single-thread MMA issuer, warps 2..5 = epilogue (one TMEM lane quarter each).
+// PERSISTENT: one CTA per SM walks the (M tile, N tile) list round-robin; the accumulator is double-buffered in TMEM
+// (2 x BLOCK_N columns), so the epilogue of tile i drains slot i&1 while the MMAs of tile i+1 fill the other slot and
+// the TMA ring keeps streaming across tile boundaries (bench: the one-tile-per-CTA form left the 256->256@32 layer at
+// 66 % of the tensor peak because load -> MMA -> epilogue ran back to back inside each CTA).
 #pragma once
 
 #include "common.cuh"
@@ -31,6 +35,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -271,7 +278,8 @@ __device__ __forceinline__ void epi_fast32(const uint32_t* __restrict__ v, const
 struct ConvTcParams {
   int B, H, W, Ci, Co, KS;
   int BW, BH, BB;            // pixel box of one M tile: BB*BH*BW == 128
-  int tiles_x, tiles_y;      // W/BW, H/BH   (grid.x = tiles_b * tiles_y * tiles_x, grid.y = Co / BLOCK_N)
+  int tiles_x, tiles_y;      // W/BW, H/BH
+  int tiles_m;               // tiles_b * tiles_y * tiles_x M tiles; the persistent grid walks tiles_m * (Co / BLOCK_N) tiles
   ConvEpilogue ep;
 };
 
@@ -280,7 +288,8 @@ struct TcConfig {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;  // power of two >= 32
+  static constexpr int kSlotCols = BLOCK_N < 32 ? 32 : BLOCK_N;  // one accumulator slot
+  static constexpr int kTmemCols = 2 * kSlotCols;                // two slots; power of two, 64..512
   // dynamic smem: [1024 align slack][stages][barriers 256B][tables]
   static size_t smem_bytes(int BB) {
     return 1024 + (size_t)STAGES * kStageBytes + 256 + (size_t)(2 + 2 * BB + 3) * BLOCK_N * sizeof(float);
@@ -300,8 +309,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2] accumulator slot complete (MMA -> epilogue)
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2] accumulator slot drained (epilogue -> MMA), 128 arrivals
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_nw = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256);
   float* s_nb = s_nw + BLOCK_N;
   float* s_d = s_nb + BLOCK_N;            // [BB][BLOCK_N] demod coefficients
@@ -311,13 +321,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile coordinates
+  // tile list: t -> (M tile, N tile) with the N tiles of one M tile adjacent (CTAs of one wave share the A boxes in L2)
   const int tiles_per_b = p.tiles_x * p.tiles_y;
-  const int tb = blockIdx.x / tiles_per_b;
-  const int tr = blockIdx.x - tb * tiles_per_b;
-  const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
-  const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
-  const int n0 = blockIdx.y * BLOCK_N;
+  const int tiles_n = p.Co / BLOCK_N;
+  const int total_tiles = p.tiles_m * tiles_n;
   const int kc_per_tap = p.Ci / BLOCK_K;
   const int num_kb = p.KS * p.KS * kc_per_tap;
   const int pad = (p.KS - 1) / 2;
@@ -329,7 +336,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
     fence_barrier_init();
   } else if (warp_id == 1) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
@@ -340,10 +350,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp_id == 0) {
-    // ===================== TMA producer =====================
-    {
-      int stage = 0;
-      uint32_t phase = 0;
+    // ===================== TMA producer: the ring runs straight through tile boundaries =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / tiles_n, n0 = (tile - tm * tiles_n) * BLOCK_N;
+      const int tb = tm / tiles_per_b;
+      const int tr = tm - tb * tiles_per_b;
+      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / kc_per_tap;
         const int c0 = (kb - tap * kc_per_tap) * BLOCK_K;
@@ -359,11 +374,17 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp_id == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
+    // ===================== MMA issuer (one elected thread) =====================
+    constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int slot = it & 1;
+      // the slot's previous tenant (tile it-2) must have been drained; the first use of each slot passes at once
+      mbar_wait(&tmem_empty_bar[slot], (uint32_t)(((it >> 1) & 1) ^ 1), 3);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(slot * Cfg::kSlotCols);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase, 1);
         tc_fence_after();
@@ -373,103 +394,119 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance the start address by k * 16 bf16 = 32 bytes inside the swizzled row (>>4 -> +2)
-            umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+      if (elect_one()) umma_commit(&tmem_full_bar[slot]);  // accumulator of this tile complete
       __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const ConvEpilogue& ep = p.ep;
     const int et = threadIdx.x - 64;  // 0..127
-    for (int i = et; i < BLOCK_N; i += 128) {
-      s_nw[i] = ep.noise ? __ldg(ep.noise_w + n0 + i) : 0.f;
-      s_nb[i] = ep.noise ? __ldg(ep.noise_b + n0 + i) : 0.f;
-    }
-    for (int i = et; i < p.BB * BLOCK_N; i += 128) {
-      const int bb = i / BLOCK_N, o = i - bb * BLOCK_N;
-      const int b = b0 + bb;
-      const bool ok = b < p.B;
-      s_d[i] = (ok && ep.dcoef) ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + o) : 1.f;
-      s_m[i] = (ok && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + o) + 1.f : 1.f;
-    }
     const bool fuse_rgb = ep.rgb_style != nullptr;   // host guarantees BB == 1 and a single N tile
-    if (fuse_rgb) {
-      for (int i = et; i < 3 * BLOCK_N; i += 128) {
-        const int o = i % BLOCK_N;
-        s_rgbw[i] = (__ldg(ep.rgb_style + (long long)b0 * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o);
-      }
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-
     const int q = warp_id & 3;          // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;        // tile row = TMEM lane
     const int xx = r % p.BW;
     const int yy = (r / p.BW) % p.BH;
     const int bb = r / (p.BW * p.BH);
-    const int b = b0 + bb, y = y0 + yy, x = x0 + xx;
-    const bool valid = b < p.B;
-    float nz = 0.f;
-    if (valid && ep.noise) {
-      const int S = ep.noise_size;
-      nz = __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
-    }
     const float* dd = s_d + bb * BLOCK_N;
     const float* mm = s_m + bb * BLOCK_N;
-    const long long pix = ((long long)b * p.H + y) * p.W + x;
-    float rgb_acc[3] = {0.f, 0.f, 0.f};
-    float* rgb_dst = nullptr;
-    if (fuse_rgb && valid) {
-      rgb_dst = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
-      if (ep.rgb_accumulate) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) rgb_acc[c] = __ldg(rgb_dst + (long long)c * p.H * p.W);
-      }
-    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int slot = it & 1;
+      const int tm = tile / tiles_n, n0 = (tile - tm * tiles_n) * BLOCK_N;
+      const int tb = tm / tiles_per_b;
+      const int tr = tm - tb * tiles_per_b;
+      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
 
-    mbar_wait(tmem_full_bar, 0, 2);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      float f[32], fr[32];
-      epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
-      if (fuse_rgb) rgb_chunk32(fr, s_rgbw + c0, BLOCK_N, rgb_acc);
-      if (valid && ep.out) {
-        if (ep.out_nchw_f32) {
-          float* out = reinterpret_cast<float*>(ep.out);
+      // per-tile operand tables (the previous tile's readers are done: they passed the barrier at the end of the loop body)
+      for (int i = et; i < BLOCK_N; i += 128) {
+        s_nw[i] = ep.noise ? __ldg(ep.noise_w + n0 + i) : 0.f;
+        s_nb[i] = ep.noise ? __ldg(ep.noise_b + n0 + i) : 0.f;
+      }
+      for (int i = et; i < p.BB * BLOCK_N; i += 128) {
+        const int tbb = i / BLOCK_N, o = i - tbb * BLOCK_N;
+        const int b = b0 + tbb;
+        const bool ok = b < p.B;
+        s_d[i] = (ok && ep.dcoef) ? __ldg(ep.dcoef + (long long)b * ep.dcoef_stride + n0 + o) : 1.f;
+        s_m[i] = (ok && ep.next_style) ? __ldg(ep.next_style + (long long)b * ep.next_style_stride + n0 + o) + 1.f : 1.f;
+      }
+      if (fuse_rgb) {
+        for (int i = et; i < 3 * BLOCK_N; i += 128) {
+          const int o = i % BLOCK_N;
+          s_rgbw[i] = (__ldg(ep.rgb_style + (long long)b0 * ep.rgb_style_stride + o) + 1.f) * __ldg(ep.rgb_w + (i / BLOCK_N) * p.Co + o);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only: tables visible
+
+      const int b = b0 + bb, y = y0 + yy, x = x0 + xx;
+      const bool valid = b < p.B;
+      float nz = 0.f;
+      if (valid && ep.noise) {
+        const int S = ep.noise_size;
+        nz = __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
+      }
+      const long long pix = ((long long)b * p.H + y) * p.W + x;
+      float rgb_acc[3] = {0.f, 0.f, 0.f};
+      float* rgb_dst = nullptr;
+      if (fuse_rgb && valid) {
+        rgb_dst = ep.rgb_out + ((long long)b * 3 * p.H + y) * p.W + x;
+        if (ep.rgb_accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
-        } else {
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+          for (int c = 0; c < 3; ++c) rgb_acc[c] = __ldg(rgb_dst + (long long)c * p.H * p.W);
+        }
+      }
+
+      mbar_wait(&tmem_full_bar[slot], (uint32_t)((it >> 1) & 1), 2);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * Cfg::kSlotCols);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float f[32], fr[32];
+        epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
+        if (fuse_rgb) rgb_chunk32(fr, s_rgbw + c0, BLOCK_N, rgb_acc);
+        if (valid && ep.out) {
+          if (ep.out_nchw_f32) {
+            float* out = reinterpret_cast<float*>(ep.out);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[(((long long)b * p.Co + n0 + c0 + j) * p.H + y) * p.W + x] = f[j];
+          } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pack(f + j, pk);
+              *reinterpret_cast<uint4*>(out + j) = pk;
+            }
+          }
+        }
+        if (valid && ep.out_raw) {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 pk;
-            pack(f + j, pk);
+            pack(fr + j, pk);
             *reinterpret_cast<uint4*>(out + j) = pk;
           }
         }
       }
-      if (valid && ep.out_raw) {
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0;
+      // all tcgen05.ld of this slot have completed (wait::ld above): hand the slot back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[slot]);
+      if (rgb_dst) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 pk;
-          pack(fr + j, pk);
-          *reinterpret_cast<uint4*>(out + j) = pk;
-        }
+        for (int c = 0; c < 3; ++c) rgb_dst[(long long)c * p.H * p.W] = rgb_acc[c];
       }
-    }
-    if (rgb_dst) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) rgb_dst[(long long)c * p.H * p.W] = rgb_acc[c];
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue thread is done with this tile's tables
     }
   }
 
@@ -541,7 +578,11 @@ int launch_conv_tc_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvTcPa
     configured = smem;
   }
   const int tiles_b = (p.B + p.BB - 1) / p.BB;
-  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)(p.Co / BLOCK_N));
+  p.tiles_m = tiles_b * p.tiles_y * p.tiles_x;
+  const long long total = (long long)p.tiles_m * (p.Co / BLOCK_N);
+  // persistent: one CTA per SM (each CTA owns 2 x BLOCK_N TMEM columns; co-resident CTAs of the narrow instantiations
+  // would still fit in the 512 columns, but one per SM keeps the allocation unconditional)
+  const unsigned grid = (unsigned)(total < (long long)num_sms() ? total : (long long)num_sms());
   kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, p);
   SX_CHECK_LAUNCH();
   return SX_OK;

@@ -29,10 +29,6 @@ namespace tc {
 
 constexpr int HALO_BW = 8, HALO_BH = 16, HALO_W = HALO_BW + 2, HALO_H = HALO_BH + 2, HALO_ROWS = HALO_W * HALO_H;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // like make_smem_desc but with an explicit stride between 8-row groups
 template <int BLOCK_K>
 __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {

@@ -329,3 +329,39 @@ def generate_images_given_dlatent(params, classify, dlatent: Tensor, class_index
     panel[:, :res] = draw_on_image(base[0].numpy())
     panel[:, res:] = draw_on_image(change[0].numpy())
     return panel, float(prob[0]), base_prob
+
+
+# --------------------------------------------------------------------------------------
+# phase A front end: encoder / discriminator
+# --------------------------------------------------------------------------------------
+def discriminator_forward(params: Dict[str, Tensor], x: Tensor) -> Tensor:
+    """DiscriminatorE.forward ST:889-909 over DiscriminatorBlock.forward ST:738-744, on a state dict with the
+    reference's keys (``blocks.i.conv_res / net.0 / net.2 / downsample.1``, ``final_conv``, ``fc``); encoder and
+    discriminator differ only in the width of ``fc`` (ST:884-887).  fq / attention blocks are default-off."""
+    n_blocks = len({k.split(".")[1] for k in params if k.startswith("blocks.")})
+    for i in range(n_blocks):
+        pre = f"blocks.{i}."
+        down = (pre + "downsample.1.weight") in params                                   # ST:733-736: all but the last
+        res = F.conv2d(x, params[pre + "conv_res.weight"], params[pre + "conv_res.bias"], stride=2 if down else 1)
+        x = leaky_relu(F.conv2d(x, params[pre + "net.0.weight"], params[pre + "net.0.bias"], padding=1))
+        x = leaky_relu(F.conv2d(x, params[pre + "net.2.weight"], params[pre + "net.2.bias"], padding=1))
+        if down:
+            x = F.conv2d(blur3x3_reflect(x), params[pre + "downsample.1.weight"], params[pre + "downsample.1.bias"],
+                         padding=1, stride=2)
+        x = (x + res) * (1 / math.sqrt(2))                                               # ST:743
+    x = F.conv2d(x, params["final_conv.weight"], params["final_conv.bias"], padding=1)  # ST:904
+    x = x.reshape(x.shape[0], -1)                                                        # Flatten ST:905
+    return F.linear(x, params["fc.weight"], params["fc.bias"]).squeeze()                 # ST:907-909
+
+
+def encode_images(enc_params: Dict[str, Tensor], classify: Callable[[Tensor], Tensor], images: Tensor,
+                  use_old_architecture: bool = True) -> Tuple[Tensor, Tensor]:
+    """NB:300-314, image by image like the notebook: w = encoder(image); logits = classify(image);
+    concat_w = cat(w, logits) (old architecture) or cat(w, softmax(logits)).  Returns (latents [N,514], logits)."""
+    lat, lgs = [], []
+    for i in range(images.shape[0]):
+        w = discriminator_forward(enc_params, images[i: i + 1]).unsqueeze(0)             # NB:306
+        lg = classify(images[i: i + 1])                                                  # NB:307
+        lat.append(torch.cat((w, lg if use_old_architecture else torch.softmax(lg, dim=1)), dim=1))
+        lgs.append(lg)
+    return torch.cat(lat), torch.cat(lgs)
