@@ -3,7 +3,8 @@
 See DESIGN.md.  Host-side mirror of the reference interface: ``modules`` (Generator, GeneratorBlock,
 RGBBlock, Conv2DMod, Blur), ``attfind`` (attfind_extraction, find_significant_styles, ...), ``counterfactual``
 (generate_change_image_given_dlatent, generate_images_given_dlatent, visualize_style), ``classifiers``
-(ResNet / MobileNet wrappers, PyTorch), ``dist`` (latent sharding + the one all-gather).  The CUDA kernels and
+(ResNet / MobileNet wrappers, PyTorch), ``stylex`` (StylEx container, encoder / discriminator, the reference's
+checkpoint format, batched phase A), ``dist`` (latent sharding + the one all-gather).  The CUDA kernels and
 the C-ABI library live under ``csrc`` (declared in ``include/stylex_b200.h``, bound in ``_native``).
 """
 from . import synthetic  # noqa: F401
@@ -15,5 +16,7 @@ from .attfind import (attfind_extraction, attfind_select, attfind_sweep, find_si
                       get_min_max_style_vectors, sindex_to_block_idx_and_index)
 from .counterfactual import (draw_on_image, generate_change_image_given_dlatent, generate_images_given_dlatent,  # noqa: F401
                              render_counterfactuals, visualize_style)
+from .stylex import (DiscriminatorBlock, DiscriminatorE, EqualLinear, StyleVectorizer, StylEx, encode_images,  # noqa: F401
+                     load_checkpoint, load_stylex, model_loader, save_checkpoint, stylex_config)
 
 __version__ = "0.1.0"

@@ -258,12 +258,12 @@ DATASET_NAMES = ("style_change", "latents", "base_prob", "minima", "maxima", "st
 def attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, dataset_name, noise, num_style_coords,
                        shift_size, discriminator_threshold, image_size=64, batch_size=1, cuda_rank=0,
                        use_discriminator=False, use_old_architecture=True, precision=None, max_batch=128,
-                       rank=0, world_size=1):
+                       rank=0, world_size=1, front_batch=256):
     """``attfind_extraction`` of NB:269-417 with the same arguments (extra keyword arguments have defaults).
 
-    Phase A (encode each image, classify it, build ``concat_w``, optional discriminator filter; NB:300-336)
-    runs the PyTorch encoder / classifier / discriminator exactly like the notebook; phases B-C are
-    ``attfind_sweep``.  Writes ``style_change_records.hdf5`` with the 9 datasets of NB:395-403 when h5py is
+    Phase A (encode each image, classify it, build ``concat_w``, discriminator output and optional filter;
+    NB:300-336) runs batched through ``stylex.encode_images`` (``front_batch`` images per launch; the dataloader
+    still yields one image per item, NB:284-285); phases B-C are ``attfind_sweep``.  Writes ``style_change_records.hdf5`` with the 9 datasets of NB:395-403 when h5py is
     importable, else ``style_change_records.npz`` with the same names; also returns them as a dict.
     """
     if batch_size != 1:
@@ -277,32 +277,36 @@ def attfind_extraction(dataloader, num_images, results_folder, stylex, classifie
     original_images = torch.zeros((num_images, 3, image_size, image_size), device=dev)
     discriminator_results = torch.zeros((num_images, 1), device=dev)
     images_found = 0
-    for batch in iter(dataloader):                                                       # NB:300
-        if images_found >= num_images:
-            break
-        batch = batch.to(dev)
-        encoder_output = stylex.encoder(batch).unsqueeze(0)                              # NB:306
-        real_classified_logits = classifier.classify_images(batch)                       # NB:307
-        if use_old_architecture:
-            concat_w_tensor = torch.cat((encoder_output, real_classified_logits), dim=1)  # NB:312
+    from .stylex import encode_images
+    have_d = use_discriminator or getattr(stylex, "D", None) is not None
+    it = iter(dataloader)                                                                # NB:298
+    exhausted = False
+    while images_found < num_images and not exhausted:
+        # the notebook handles one image per iteration (NB:300-336); here up to `front_batch` images go through the
+        # encoder, the classifier, the generator and the discriminator together -- same arithmetic per image, and the
+        # images that pass the filter are kept in dataloader order, exactly like the sequential loop
+        chunk = []
+        for batch in it:
+            chunk.append(batch.to(dev).reshape(-1, 3, image_size, image_size))
+            if len(chunk) >= min(front_batch, num_images - images_found):
+                break
         else:
-            concat_w_tensor = torch.cat((encoder_output, torch.softmax(real_classified_logits, dim=1)), dim=1)
-        skip, discriminator_output = None, torch.zeros(1, device=dev)
-        if use_discriminator or getattr(stylex, "D", None) is not None:
-            w_latent_tensor = styles_def_to_tensor([(concat_w_tensor, G.num_layers)])
-            generated_image = G(w_latent_tensor, noise)
-            if use_old_architecture:
-                skip, discriminator_output = discriminator_filter(stylex.D, generated_image, discriminator_threshold)
-            else:
-                skip, discriminator_output = discriminator_filter(
-                    stylex.D, generated_image, discriminator_threshold,
-                    probabilities=torch.softmax(classifier.classify_images(generated_image), dim=1))
-        if use_discriminator and skip:
-            continue
-        original_images[images_found] = batch
-        image_latents[images_found] = concat_w_tensor
-        discriminator_results[images_found] = discriminator_output
-        images_found += 1
+            exhausted = True
+        if not chunk:
+            break
+        x = torch.cat(chunk)
+        fe = encode_images(stylex, classifier, x, noise, batch=front_batch, use_old_architecture=use_old_architecture,
+                           discriminator=have_d)
+        keep = torch.ones(x.shape[0], dtype=torch.bool, device=dev)
+        if use_discriminator and discriminator_threshold is not None:
+            keep = ~(fe["discriminator"][:, 0] < discriminator_threshold)                # NB:262-266: skip when output < threshold
+        idx = keep.nonzero().flatten()[: num_images - images_found]
+        k = int(idx.numel())
+        original_images[images_found: images_found + k] = x[idx]
+        image_latents[images_found: images_found + k] = fe["latents"][idx]
+        if have_d:
+            discriminator_results[images_found: images_found + k] = fe["discriminator"][idx]
+        images_found += k
     if images_found == 0:
         raise ValueError('No images pass the threshold check')
     res = attfind_sweep(G, classifier, image_latents[:images_found], noise, shift_size=shift_size, precision=precision,

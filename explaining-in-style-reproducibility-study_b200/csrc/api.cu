@@ -105,9 +105,7 @@ int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, fl
     dp.dcoef = dcoef;
     dp.dcoef_stride = Co;
     dp.eps = eps;
-    dim3 grid((Co + 127) / 128, B, 1);
-    demod_kernel<<<grid, 128, Ci * sizeof(float), st>>>(dp);
-    SX_CHECK_LAUNCH();
+    SX_TRY(launch_demod(dp, B, Ci, Co, st));
   }
   if (precision == SX_PREC_FP32) {
     ConvSimtParams p;

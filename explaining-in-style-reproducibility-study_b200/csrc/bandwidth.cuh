@@ -458,21 +458,59 @@ struct DemodParams {
   int dcoef_stride;
   float eps;
 };
-__global__ void __launch_bounds__(128) demod_kernel(DemodParams p) {
+// One CTA = 128 output channels x DEMOD_BPC samples: every wsq element fetched from L2 serves DEMOD_BPC samples (the
+// one-sample-per-CTA form re-read the conv's whole wsq matrix per sample -- 2 GB of L2 traffic per 256-sample launch,
+// 90 us).  Per sample the accumulation order over i is unchanged, so the coefficients are bit-identical.
+constexpr int DEMOD_BPC = 8;
+__global__ void __launch_bounds__(128) demod_kernel(DemodParams p, int B) {
   const DemodConv cv = p.conv[p.first_conv + blockIdx.z];
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  extern __shared__ float s_s2[];  // (style+1)^2 of this sample for this conv
-  const float* s = p.styles + (long long)b * p.style_stride + cv.soff;
-  for (int i = threadIdx.x; i < cv.ci; i += blockDim.x) {
-    const float t = __ldg(s + i) + 1.f;
-    s_s2[i] = t * t;
+  const int b0 = blockIdx.y * DEMOD_BPC;
+  if (blockIdx.x * blockDim.x >= cv.co) return;   // whole CTA out of range for this (narrower) conv
+  extern __shared__ float s_s2[];  // [ci][DEMOD_BPC]: (style+1)^2 of the CTA's samples for this conv
+  for (int t = threadIdx.x; t < cv.ci * DEMOD_BPC; t += blockDim.x) {
+    const int k = t / cv.ci, i = t - k * cv.ci;
+    const int b = b0 + k;
+    float v = 0.f;
+    if (b < B) {
+      v = __ldg(p.styles + (long long)b * p.style_stride + cv.soff + i) + 1.f;
+      v *= v;
+    }
+    s_s2[i * DEMOD_BPC + k] = v;
   }
   __syncthreads();
   if (o >= cv.co) return;
-  float acc = 0.f;
-  for (int i = 0; i < cv.ci; ++i) acc = fmaf(s_s2[i], __ldg(cv.wsq + (long long)i * cv.co + o), acc);
-  p.dcoef[(long long)b * p.dcoef_stride + cv.doff + o] = rsqrtf(acc + p.eps);
+  float acc[DEMOD_BPC];
+#pragma unroll
+  for (int k = 0; k < DEMOD_BPC; ++k) acc[k] = 0.f;
+  // 16 independent L2 loads in flight per thread: with the loads issued one per iteration this loop ran at L2 latency
+#pragma unroll 16
+  for (int i = 0; i < cv.ci; ++i) {
+    const float w = __ldg(cv.wsq + (long long)i * cv.co + o);
+    const float4 sa = *reinterpret_cast<const float4*>(s_s2 + i * DEMOD_BPC);
+    const float4 sb = *reinterpret_cast<const float4*>(s_s2 + i * DEMOD_BPC + 4);
+    acc[0] = fmaf(sa.x, w, acc[0]); acc[1] = fmaf(sa.y, w, acc[1]); acc[2] = fmaf(sa.z, w, acc[2]); acc[3] = fmaf(sa.w, w, acc[3]);
+    acc[4] = fmaf(sb.x, w, acc[4]); acc[5] = fmaf(sb.y, w, acc[5]); acc[6] = fmaf(sb.z, w, acc[6]); acc[7] = fmaf(sb.w, w, acc[7]);
+  }
+#pragma unroll
+  for (int k = 0; k < DEMOD_BPC; ++k)
+    if (b0 + k < B) p.dcoef[(long long)(b0 + k) * p.dcoef_stride + cv.doff + o] = rsqrtf(acc[k] + p.eps);
+}
+
+inline int launch_demod(const DemodParams& dp, int B, int max_ci, int max_co, cudaStream_t st) {
+  if (B == 0 || dp.num_convs == 0) return SX_OK;
+  const size_t smem = (size_t)max_ci * DEMOD_BPC * sizeof(float);
+  SX_REQUIRE(smem <= 200 * 1024, "demod: Ci=%d too large for the shared-memory style table", max_ci);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    SX_CUDA(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((max_co + 127) / 128, (B + DEMOD_BPC - 1) / DEMOD_BPC, dp.num_convs);
+  SX_REQUIRE(grid.y <= 65535, "demod: batch too large");
+  demod_kernel<<<grid, 128, smem, st>>>(dp, B);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
 }
 
 // =================================================================================================

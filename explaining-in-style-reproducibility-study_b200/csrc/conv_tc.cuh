@@ -466,11 +466,30 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       mbar_wait(&tmem_full_bar[slot], (uint32_t)((it >> 1) & 1), 2);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * Cfg::kSlotCols);
+      // generator layers (leaky-ReLU, bf16 NHWC output): packed fp32x2 arithmetic, two columns per instruction
+      const bool fast = ep.act && !ep.out_nchw_f32;
+      uint64_t racc[3] = {0ull, 0ull, 0ull};
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_d + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (fast) {
+          uint32_t om[16], orw[16];
+          if (fuse_rgb) epi_fast32<true>(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, om, orw, s_rgbw + c0, BLOCK_N, racc);
+          else epi_fast32<false>(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, om, orw, nullptr, 0, racc);
+          if (valid && ep.out) {
+            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + pix * p.Co + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = make_uint4(om[4 * j], om[4 * j + 1], om[4 * j + 2], om[4 * j + 3]);
+          }
+          if (valid && ep.out_raw) {
+            uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + pix * p.Co + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j] = make_uint4(orw[4 * j], orw[4 * j + 1], orw[4 * j + 2], orw[4 * j + 3]);
+          }
+          continue;
+        }
         float f[32], fr[32];
         epi_chunk32(v, dd + c0, s_nw + c0, s_nb + c0, mm + c0, nz, ep.act, !ep.out_nchw_f32, f, fr);
         if (fuse_rgb) rgb_chunk32(fr, s_rgbw + c0, BLOCK_N, rgb_acc);
@@ -504,7 +523,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_kernel(const __grid_const
       mbar_arrive(&tmem_empty_bar[slot]);
       if (rgb_dst) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) rgb_dst[(long long)c * p.H * p.W] = rgb_acc[c];
+        for (int c = 0; c < 3; ++c) {
+          float lo, hi;
+          upk2(racc[c], lo, hi);   // zero unless the packed epilogue ran (even / odd column partial sums)
+          rgb_dst[(long long)c * p.H * p.W] = rgb_acc[c] + (lo + hi);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue thread is done with this tile's tables
     }

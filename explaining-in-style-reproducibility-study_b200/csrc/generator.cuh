@@ -253,9 +253,7 @@ int generator_forward_t(sx_generator* g, const float* styles, const float* inois
     dp.dcoef_stride = g->demod_row;
     dp.eps = 1e-8f;
     ProfScope ps(35, 0, 0, st);
-    dim3 grid((max_co + 127) / 128, B, dp.num_convs);
-    demod_kernel<<<grid, 128, max_ci * sizeof(float), st>>>(dp);
-    SX_CHECK_LAUNCH();
+    SX_TRY(launch_demod(dp, B, max_ci, max_co, st));
   }
 
   const int start_block = start_conv / 2;

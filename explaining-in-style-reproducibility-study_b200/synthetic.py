@@ -70,6 +70,40 @@ def make_generator_state(image_size: int, seed: int = 42, latent_dim: int = 514,
     return sd
 
 
+def discriminator_filters(image_size: int, network_capacity: int = 16, fmap_max: int = 512) -> List[Tuple[int, int]]:
+    """[(Ci, Co)] per DiscriminatorBlock -- reference stylex_train.py:846-853."""
+    num_layers = int(math.log2(image_size) - 1)
+    filters = [3] + [min(fmap_max, (network_capacity * 4) * (2 ** i)) for i in range(num_layers + 1)]
+    return list(zip(filters[:-1], filters[1:]))
+
+
+def make_discriminator_state(image_size: int, seed: int = 42, network_capacity: int = 16, fmap_max: int = 512,
+                             encoder: bool = False, encoder_dim: int = 512) -> "OrderedDict[str, torch.Tensor]":
+    """State dict with the reference DiscriminatorE's key names (stylex_train.py:721-744, 842-887; SURVEY.md
+    Appendix B), kaiming weights + uniform biases like nn.Conv2d / nn.Linear under StylEx._init_weights."""
+    g = torch.Generator().manual_seed(seed + 3000017)
+    pairs = discriminator_filters(image_size, network_capacity, fmap_max)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def conv(key, co, ci, k):
+        sd[key + ".weight"] = _kaiming(g, co, ci, k, k)
+        sd[key + ".bias"] = _bias(g, co, ci * k * k)
+
+    for i, (ci, co) in enumerate(pairs):
+        p = f"blocks.{i}."
+        conv(p + "conv_res", co, ci, 1)
+        conv(p + "net.0", co, ci, 3)
+        conv(p + "net.2", co, co, 3)
+        if i != len(pairs) - 1:
+            conv(p + "downsample.1", co, co, 3)
+    c = pairs[-1][1]
+    conv("final_conv", c, c, 3)
+    out_dim = encoder_dim if encoder else 1
+    sd["fc.weight"] = _kaiming(g, out_dim, 4 * c)
+    sd["fc.bias"] = _bias(g, out_dim, 4 * c)
+    return sd
+
+
 def make_latents(n: int, seed: int = 42, latent_dim: int = 514) -> torch.Tensor:
     """w[N,512] ~ N(0,1) (+) 2 'classifier logits' ~ N(0,1): the concat_w_tensor of the notebook."""
     g = torch.Generator().manual_seed(seed + 1000003)

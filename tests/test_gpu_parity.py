@@ -379,7 +379,7 @@ def test_attfind_extraction_entry_point(dev, tmp_path):
 
     class Enc(torch.nn.Module):
         def forward(self, img):
-            return torch.nn.functional.adaptive_avg_pool2d(img, 16).reshape(-1)[:512] * 0.5
+            return (torch.nn.functional.adaptive_avg_pool2d(img, 16).reshape(img.shape[0], -1)[:, :512] * 0.5).squeeze()
 
     class Stylex:
         pass
@@ -575,3 +575,81 @@ def test_native_launches_counted(dev):
     before = _native.launch_count()
     sx.modules.upsample2x(torch.zeros(1, 1, 4, 4, device=dev))
     assert _native.launch_count() == before + 1
+
+
+# ---- phase A front end + StylEx container -----------------------------------
+def _frontend(z, dev):
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    enc = sx.DiscriminatorE(size, cap, encoder=True)
+    dis = sx.DiscriminatorE(size, cap)
+    assert not enc.load_state_dict(synthetic.make_discriminator_state(size, seed=21, network_capacity=cap, encoder=True), strict=False).unexpected_keys
+    assert not dis.load_state_dict(synthetic.make_discriminator_state(size, seed=22, network_capacity=cap), strict=False).unexpected_keys
+    G = g_module(synthetic.make_generator_state(size, seed=23, network_capacity=cap), size, cap, dev)
+
+    class Stylex:
+        pass
+
+    st = Stylex()
+    st.G, st.encoder, st.D = G, enc.to(dev).eval(), dis.to(dev).eval()
+    clf = sx.make_classifier("mobilenet", tiny_cnn_from(z, "clf.").to(dev), size)
+    return size, st, clf
+
+
+def test_encoder_discriminator_match_reference_golden(dev, golden):
+    """DiscriminatorE (cuDNN convolutions + the native blur) against the executed reference, batch and single image."""
+    z = golden("frontend_small.npz")
+    _, st, _ = _frontend(z, dev)
+    images = torch.from_numpy(z["images"]).to(dev)
+    before = _native.launch_count()
+    e = st.encoder(images)
+    assert _native.launch_count() - before == 3                      # one native blur per down-sampling block
+    assert float((e.cpu() - torch.from_numpy(z["enc_batch"])).abs().max()) <= FP32_TOL
+    assert float((st.D(images).cpu() - torch.from_numpy(z["dis_batch"])).abs().max()) <= FP32_TOL
+    single = st.encoder(images[:1])
+    assert single.shape == (512,)
+    assert float((single.cpu() - torch.from_numpy(z["enc_single"])).abs().max()) <= FP32_TOL
+    assert st.D(images[:1]).shape == ()
+
+
+def test_attfind_extraction_phase_a_matches_verbatim_notebook(dev, golden, tmp_path):
+    """the notebook-signature entry point with the real encoder / discriminator in place: the batched phase A gives the
+    datasets the VERBATIM notebook loop wrote (tests/golden/frontend_small.npz)."""
+    z = golden("frontend_small.npz")
+    size, st, clf = _frontend(z, dev)
+    images = [torch.from_numpy(z["images"][i: i + 1]) for i in range(z["images"].shape[0])]
+    noise = torch.from_numpy(z["noise"]).to(dev)
+    n = len(images)
+    out = sx.attfind_extraction(images + images[:1], n, str(tmp_path), st, clf, None, noise, st.G.num_style_coords, 1.0, -0.5,
+                                image_size=size, batch_size=1, cuda_rank=0, front_batch=4)     # 5 images: chunks of 4 + 1
+    for k in ("latents", "base_prob", "style_coordinates", "discriminator", "original_images", "minima", "maxima"):
+        ref = torch.from_numpy(z["nb." + k])
+        assert out[k].shape == ref.shape, k
+        assert float((out[k].cpu() - ref).abs().max()) <= FP32_TOL, k
+    tot = float(out["style_change"].abs().sum())
+    assert abs(tot - float(z["nb.style_change_abs_sum"])) <= 1e-3 * float(z["nb.style_change_abs_sum"])
+    # the discriminator filter (NB:262-266, 327-328): images whose output is below the threshold are skipped, order kept
+    d = z["nb.discriminator"][:, 0]
+    thr = float(np.sort(d)[2]) - 1e-3                                   # keeps the 3 highest
+    want = [i for i in range(n) if not d[i] < thr]
+    out2 = sx.attfind_extraction(images, len(want), None, st, clf, None, noise, st.G.num_style_coords, 1.0, thr,
+                                 image_size=size, use_discriminator=True, front_batch=2)
+    assert float((out2["latents"].cpu() - torch.from_numpy(z["nb.latents"][want])).abs().max()) <= FP32_TOL
+    assert float((out2["discriminator"].cpu()[:, 0] - torch.from_numpy(d[want])).abs().max()) <= FP32_TOL
+
+
+def test_stylex_container_checkpoint_on_device(dev, tmp_path):
+    """StylEx container: reference-format checkpoint -> device model whose G / encoder / D run the native path."""
+    torch.manual_seed(5)
+    m = sx.StylEx(image_size=16, network_capacity=4)
+    assert next(m.parameters()).is_cuda                                  # ST:965
+    path = sx.save_checkpoint(m, tmp_path, "default", 7, sx.stylex_config(16, network_capacity=4))
+    m2 = sx.load_stylex(path, 16, network_capacity=4)
+    img = torch.rand(3, 3, 16, 16, device=dev)
+    w = m2.encoder(img)
+    assert w.shape == (3, 512) and torch.equal(w, m.eval().encoder(img))
+    lat = torch.cat([w, torch.zeros(3, 2, device=dev)], dim=1)
+    noise = synthetic.make_noise(16, 1).to(dev)
+    rgb = m2.G(sx.styles_def_to_tensor([(lat, m2.G.num_layers)]), noise)
+    assert rgb.shape == (3, 3, 16, 16) and torch.isfinite(rgb).all()
+    assert m2.D(rgb).shape == (3,)
+    assert torch.equal(m2.GE(sx.styles_def_to_tensor([(lat, m2.G.num_layers)]), noise), rgb)   # GE == G after reset_parameter_averaging

@@ -178,3 +178,50 @@ def test_s2d_stem_weights_reproduce_the_7x7_stride2_conv():
         got = torch.nn.functional.conv2d(space_to_depth_input(x), stem_weight_to_s2d(w), None, 1, 0)
         assert got.shape == ref.shape
         assert float((got - ref).abs().max()) <= 1e-4
+
+
+# ---- StylEx container + the reference's checkpoint format -------------
+def test_stylex_state_dict_matches_reference_manifest():
+    """our StylEx(image_size=64) has exactly the keys and shapes of the reference's (tests/golden/stylex_keys.json,
+    written from the imported reference class), so a reference model_<n>.pt loads with strict=True."""
+    import json
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "stylex_keys.json")))
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False          # keep the container on the CPU here
+    try:
+        m = sx.StylEx(image_size=man["image_size"])
+    finally:
+        torch.cuda.is_available = real
+    ours = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(ours) == list(man["state_dict"]), set(ours) ^ set(man["state_dict"])
+    assert ours == man["state_dict"]
+    assert sx.stylex.__reference_version__ == man["version"]
+    assert sorted(sx.stylex_config(64)) == sorted(man["config_keys"])
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """Trainer.save / Trainer.load layout (ST:1736-1774): models/<name>/model_<n>.pt with {'StylEx', 'version'} and
+    models/<name>/.config.json; load(-1) picks the highest number and builds the model the config describes."""
+    import json
+    torch.manual_seed(3)
+    m = sx.StylEx(image_size=16, network_capacity=4, rank=0) if not torch.cuda.is_available() else sx.StylEx(16, network_capacity=4).cpu()
+    cfg = sx.stylex_config(16, network_capacity=4)
+    sx.save_checkpoint(m, tmp_path / "models", "run", 3, cfg)
+    with torch.no_grad():
+        m.G.blocks[0].conv1.weight.add_(1.0)
+    path = sx.save_checkpoint(m, tmp_path / "models", "run", 12, cfg)
+    assert path.endswith(os.path.join("models", "run", "model_12.pt"))
+    assert json.loads((tmp_path / "models" / "run" / ".config.json").read_text()) == cfg
+    data = torch.load(path, map_location="cpu")
+    assert set(data) == {"StylEx", "version"}
+    m2, cfg2 = sx.load_checkpoint(tmp_path / "models", "run", -1)
+    assert cfg2 == cfg and not m2.training
+    for (k, a), (k2, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k == k2 and torch.equal(a.cpu(), b.cpu()), k
+    m3, _ = sx.load_checkpoint(tmp_path / "models", "run", 3)
+    assert not torch.equal(m3.G.blocks[0].conv1.weight.cpu(), m2.G.blocks[0].conv1.weight.cpu())
+    # without .config.json the architecture is read off the tensors
+    (tmp_path / "models" / "run" / ".config.json").unlink()
+    m4, cfg4 = sx.load_checkpoint(tmp_path / "models", "run", 12)
+    assert cfg4["image_size"] == 16 and cfg4["network_capacity"] == 4
+    assert torch.equal(m4.encoder.fc.weight.cpu(), m.encoder.fc.weight.cpu())

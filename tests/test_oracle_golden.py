@@ -116,3 +116,44 @@ def test_sindex_mapping():
     assert O.sindex_to_block_idx_and_index(pairs, 1023) == (0, 1023)
     assert O.sindex_to_block_idx_and_index(pairs, 1024) == (1, 0)
     assert O.sindex_to_block_idx_and_index(pairs, 2463) == (4, 95)
+
+
+# ---- phase A front end ------------------------------------------------------
+def _frontend_states(z):
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    enc_sd = synthetic.make_discriminator_state(size, seed=21, network_capacity=cap, encoder=True)
+    dis_sd = synthetic.make_discriminator_state(size, seed=22, network_capacity=cap)
+    g_sd = synthetic.make_generator_state(size, seed=23, network_capacity=cap)
+    fp = np.array([float(enc_sd["fc.weight"].double().sum()), float(dis_sd["blocks.0.net.0.weight"].double().abs().sum()),
+                   float(g_sd["blocks.0.conv1.weight"].double().sum())])
+    assert np.allclose(fp, z["fp"], rtol=1e-9, atol=1e-6), "torch CPU RNG drifted: seeded weights differ"
+    return size, cap, enc_sd, dis_sd, g_sd
+
+
+def test_encoder_discriminator_match_reference(golden):
+    z = golden("frontend_small.npz")
+    _, _, enc_sd, dis_sd, _ = _frontend_states(z)
+    images = torch.from_numpy(z["images"])
+    assert np.abs(O.discriminator_forward(enc_sd, images).numpy() - z["enc_batch"]).max() <= 2e-6
+    assert np.abs(O.discriminator_forward(dis_sd, images).numpy() - z["dis_batch"]).max() <= 2e-6
+    single = O.discriminator_forward(enc_sd, images[:1])
+    assert single.shape == z["enc_single"].shape == (512,)                 # the squeeze of ST:909
+    assert np.abs(single.numpy() - z["enc_single"]).max() <= 2e-6
+    assert O.discriminator_forward(dis_sd, images[:1]).shape == z["dis_single"].shape == ()
+
+
+def test_phase_a_matches_verbatim_notebook(golden):
+    z = golden("frontend_small.npz")
+    size, cap, enc_sd, dis_sd, g_sd = _frontend_states(z)
+    model = tiny_cnn_from(z, "clf.")
+    clf = classifiers.make_classifier("mobilenet", model, size)
+    images = torch.from_numpy(z["images"])
+    lat, logits = O.encode_images(enc_sd, clf.classify_images, images)
+    assert np.abs(lat.numpy() - z["nb.latents"]).max() <= 2e-6
+    L = len(O.generator_layout(g_sd))
+    noise = torch.from_numpy(z["noise"])
+    gen, sc = O.generator_forward(g_sd, O.styles_def_to_tensor([(lat, L)]), noise, get_style_coords=True)
+    assert np.abs(sc.numpy() - z["nb.style_coordinates"]).max() <= 5e-6
+    assert np.abs(clf.classify_images(gen).numpy() - z["nb.base_prob"]).max() <= 1e-5
+    d = torch.stack([O.discriminator_forward(dis_sd, gen[i: i + 1]) for i in range(gen.shape[0])])
+    assert np.abs(d.numpy() - z["nb.discriminator"][:, 0]).max() <= 1e-5
