@@ -9,7 +9,7 @@ the C-ABI library live under ``csrc`` (declared in ``include/stylex_b200.h``, bo
 """
 from . import synthetic  # noqa: F401
 from . import _native  # noqa: F401
-from .modules import (Blur, Conv2DMod, Generator, GeneratorBlock, GeneratorPlan, RGBBlock, image_noise,  # noqa: F401
+from .modules import (Blur, Conv2DMod, Conv2DModFunction, Generator, GeneratorBlock, GeneratorPlan, RGBBlock, image_noise,  # noqa: F401
                       styles_def_to_tensor)
 from .classifiers import MobileNet, ResNet, make_classifier  # noqa: F401
 from .attfind import (attfind_extraction, attfind_select, attfind_sweep, find_significant_styles,  # noqa: F401

@@ -6,6 +6,7 @@
 #include "attfind.cuh"
 #include "bandwidth.cuh"
 #include "common.cuh"
+#include "conv_bwd.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc_halo.cuh"
@@ -117,6 +118,110 @@ int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, fl
   }
   return tc::launch_conv_bf16(reinterpret_cast<__nv_bfloat16*>(ws + L.xmod), reinterpret_cast<__nv_bfloat16*>(ws + L.wpk), B, Ci, Co,
                             H, W, k, ep, st);
+}
+
+// ---- Conv2DMod backward (first order) -- conv_bwd.cuh ---------------------------------------------------------
+struct Conv2dModBwdWs {
+  size_t gz, xm, wT, wsq, dcoef, gdot, gm1, msq, partial, total;
+  int splits;
+};
+static Conv2dModBwdWs conv2dmod_bwd_ws(int B, int Ci, int Co, int H, int W, int k) {
+  Conv2dModBwdWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t HW = (size_t)H * W;
+  w.splits = wgrad_splits(B, Ci, Co, H, W, k);
+  w.gz = take((size_t)B * HW * Co * 4);
+  w.xm = take((size_t)B * HW * Ci * 4);
+  w.wT = take((size_t)k * k * Ci * Co * 4);
+  w.wsq = take((size_t)Ci * Co * 4);
+  w.dcoef = take((size_t)B * Co * 4);
+  w.gdot = take((size_t)B * Co * 4);
+  w.gm1 = take((size_t)B * Ci * 4);
+  w.msq = take((size_t)B * Ci * 4);
+  w.partial = take((size_t)w.splits * k * k * Co * Ci * 4);
+  w.total = off;
+  return w;
+}
+
+size_t sx_conv2dmod_bwd_workspace_bytes(int B, int Ci, int Co, int H, int W, int k) {
+  if (B < 1 || Ci < 1 || Co < 1 || H < 1 || W < 1 || k < 1) return 0;
+  return conv2dmod_bwd_ws(B, Ci, Co, H, W, k).total;
+}
+
+int sx_conv2dmod_bwd(const float* x, const float* weight, const float* style, const float* out, const float* grad_out,
+                     float* grad_x, float* grad_weight, float* grad_style, int B, int Ci, int Co, int H, int W, int k,
+                     int demod, float eps, void* workspace, size_t ws_bytes, sx_stream_t stream) {
+  SX_REQUIRE(B >= 0 && Ci >= 1 && Co >= 1 && H >= 1 && W >= 1, "bad shape B=%d Ci=%d Co=%d H=%d W=%d", B, Ci, Co, H, W);
+  SX_REQUIRE(k == 1 || k == 3, "kernel size %d not supported (1 or 3)", k);
+  SX_REQUIRE(grad_weight, "null argument");
+  cudaStream_t st = S(stream);
+  if (B == 0) {   // empty batch: the weight gradient is zero, nothing else to write
+    SX_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)Co * Ci * k * k * 4, st));
+    return SX_OK;
+  }
+  SX_REQUIRE(x && weight && style && grad_out && grad_x && grad_style && workspace, "null argument");
+  SX_REQUIRE(!demod || out, "demod backward needs the forward output");
+  SX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  const Conv2dModBwdWs L = conv2dmod_bwd_ws(B, Ci, Co, H, W, k);
+  if (ws_bytes < L.total) return fail(SX_ENOMEM, "workspace %zu bytes < required %zu", ws_bytes, L.total);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  float *gz = F(L.gz), *xm = F(L.xm), *wT = F(L.wT), *wsq = F(L.wsq), *dcoef = F(L.dcoef), *gdot = F(L.gdot), *gm1 = F(L.gm1),
+        *msq = F(L.msq), *partial = F(L.partial);
+  const int HW = H * W, taps = k * k;
+  // packed operands: wsq[i][o], flipped / transposed weights for the dgrad
+  pack_weights_kernel<<<ew_grid((long long)Ci * Co, 256), 256, 0, st>>>(weight, nullptr, nullptr, wsq, Co, Ci, taps);
+  SX_CHECK_LAUNCH();
+  pack_weights_dgrad_kernel<<<ew_grid((long long)Ci * Co, 256), 256, 0, st>>>(weight, wT, Co, Ci, taps);
+  SX_CHECK_LAUNCH();
+  if (demod) {
+    DemodParams dp{};
+    dp.conv[0] = DemodConv{wsq, Ci, Co, 0, 0};
+    dp.first_conv = 0; dp.num_convs = 1; dp.styles = style; dp.style_stride = Ci; dp.dcoef = dcoef; dp.dcoef_stride = Co; dp.eps = eps;
+    SX_TRY(launch_demod(dp, B, Ci, Co, st));
+  }
+  // gz = g * d (NHWC)
+  nchw_to_nhwc_scale_kernel<<<dim3((HW + 31) / 32, (Co + 31) / 32, B), 256, 0, st>>>(grad_out, demod ? dcoef : nullptr, gz, Co, HW);
+  SX_CHECK_LAUNCH();
+  // dgrad: gxm = conv(W^T flipped, gz) -> grad_x (NCHW), then gm1 = <gxm, x> per plane and grad_x *= m in place
+  {
+    ConvSimtParams p;
+    p.x = gz; p.x_bstride = (long long)HW * Co; p.wpk = wT;
+    p.B = B; p.Ci = Co; p.Co = Ci; p.H = H; p.W = W; p.KS = k;
+    ConvEpilogue ep{};
+    ep.out = grad_x; ep.out_nchw_f32 = 1;
+    p.ep = ep;
+    SX_TRY(launch_conv_simt(p, st));
+  }
+  plane_dot_kernel<<<(unsigned)((long long)B * Ci), 256, 0, st>>>(grad_x, x, style, gm1, HW);
+  SX_CHECK_LAUNCH();
+  if (demod) {
+    plane_dot_kernel<<<(unsigned)((long long)B * Co), 256, 0, st>>>(const_cast<float*>(grad_out), out, nullptr, gdot, HW);
+    SX_CHECK_LAUNCH();
+    const long long n = (long long)B * (Ci > Co ? Ci : Co);
+    demod_grad_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gdot, dcoef, (long long)B * Co, style, msq, (long long)B * Ci);
+    SX_CHECK_LAUNCH();
+  }
+  style_grad_kernel<<<(unsigned)(((long long)B * Ci * 32 + 255) / 256), 256, 0, st>>>(gm1, style, demod ? gdot : nullptr, wsq, grad_style, B, Ci, Co);
+  SX_CHECK_LAUNCH();
+  // wgrad over the modulated activations
+  nchw_to_nhwc_modulate_kernel<float><<<dim3((HW + 31) / 32, (Ci + 31) / 32, B), 256, 0, st>>>(x, style, xm, Ci, HW);
+  SX_CHECK_LAUNCH();
+  {
+    WgradParams p;
+    p.gz = gz; p.xm = xm; p.partial = partial;
+    p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KS = k; p.splits = L.splits;
+    const long long M = (long long)B * HW;
+    p.pix_per_split = ((M + L.splits - 1) / L.splits + 15) / 16 * 16;
+    dim3 grid((unsigned)(((Co + 63) / 64) * ((Ci + 63) / 64)), (unsigned)taps, (unsigned)L.splits);
+    wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
+    SX_CHECK_LAUNCH();
+  }
+  wgrad_reduce_kernel<<<ew_grid((long long)Co * Ci, 256), 256, 0, st>>>(partial, L.splits, weight, demod ? gdot : nullptr, msq, grad_weight,
+                                                                      B, Co, Ci, taps);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
 }
 
 int sx_upsample2x_bilinear(const float* x, float* out, int B, int C, int H, int W, sx_stream_t stream) {

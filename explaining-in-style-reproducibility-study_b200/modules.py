@@ -141,20 +141,62 @@ class Conv2DMod(nn.Module):
             raise NotImplementedError("stylex_b200 Conv2DMod: only stride=1, dilation=1 (all the reference ever uses)")
         N.require_cuda(x, y, self.weight)
         N.device_check()
-        x, y, w = N.f32c(x), N.f32c(y), N.f32c(self.weight.detach())
-        b, c, h, wd = x.shape
-        co, ci, k, _ = w.shape
+        b, c = x.shape[:2]
+        co, ci, k, _ = self.weight.shape
         if c != ci or y.shape != (b, ci):
-            raise ValueError(f"Conv2DMod: x {tuple(x.shape)} / style {tuple(y.shape)} do not match weight {tuple(w.shape)}")
-        prec = _prec(self)
-        lib = N.lib()
-        nbytes = lib.sx_conv2dmod_workspace_bytes(b, ci, co, h, wd, k, prec)
-        ws = _op_ws.get(nbytes, x.device)
-        out = torch.empty(b, co, h, wd, device=x.device, dtype=torch.float32)
-        N.check(lib.sx_conv2dmod_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), out.data_ptr(), b, ci, co, h, wd, k,
-                                     1 if self.demod else 0, float(self.eps), prec, ws.data_ptr(), ws.numel(),
-                                     N.stream_ptr()), "sx_conv2dmod_fwd")
+            raise ValueError(f"Conv2DMod: x {tuple(x.shape)} / style {tuple(y.shape)} do not match weight {tuple(self.weight.shape)}")
+        if (_prec(self) == N.PREC_FP32 and torch.is_grad_enabled()
+                and (x.requires_grad or y.requires_grad or self.weight.requires_grad)):
+            # training: the native forward + the native first-order backward (sx_conv2dmod_bwd).  The backward kernels are
+            # fp32; the bf16 module records no graph (inference precision, as before).
+            return Conv2DModFunction.apply(x, y, self.weight, bool(self.demod), float(self.eps))
+        return _conv2dmod_forward(x, y, self.weight.detach(), bool(self.demod), float(self.eps), _prec(self))
+
+
+def _conv2dmod_forward(x, y, w, demod, eps, prec):
+    x, y, w = N.f32c(x), N.f32c(y), N.f32c(w)
+    b, ci, h, wd = x.shape
+    co, _, k, _ = w.shape
+    lib = N.lib()
+    nbytes = lib.sx_conv2dmod_workspace_bytes(b, ci, co, h, wd, k, prec)
+    ws = _op_ws.get(nbytes, x.device)
+    out = torch.empty(b, co, h, wd, device=x.device, dtype=torch.float32)
+    N.check(lib.sx_conv2dmod_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), out.data_ptr(), b, ci, co, h, wd, k,
+                                 1 if demod else 0, eps, prec, ws.data_ptr(), ws.numel(), N.stream_ptr()), "sx_conv2dmod_fwd")
+    return out
+
+
+class Conv2DModFunction(torch.autograd.Function):
+    """Conv2DMod.forward (ST:647-667) with its first-order backward on the native kernels (``csrc/conv_bwd.cuh``):
+    grad_x (dgrad through the shared weights), grad_weight (wgrad over all pixels of the batch + the demodulation term)
+    and grad_style (modulation + demodulation terms).  Not twice differentiable: the path-length and gradient penalties
+    of the training step (ST:296-316) need a double backward that is not built."""
+
+    @staticmethod
+    def forward(ctx, x, y, weight, demod, eps):
+        xd, yd, wdt = N.f32c(x.detach()), N.f32c(y.detach()), N.f32c(weight.detach())
+        out = _conv2dmod_forward(xd, yd, wdt, demod, eps, N.PREC_FP32)
+        ctx.save_for_backward(xd, yd, wdt, out)
+        ctx.demod, ctx.eps = demod, eps
         return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        x, y, w, out = ctx.saved_tensors
+        N.require_cuda(grad_out)
+        g = N.f32c(grad_out)
+        b, ci, h, wd = x.shape
+        co, _, k, _ = w.shape
+        lib = N.lib()
+        gx = torch.empty_like(x)
+        gy = torch.empty_like(y)
+        gw = torch.empty_like(w)
+        ws = _op_ws.get(lib.sx_conv2dmod_bwd_workspace_bytes(b, ci, co, h, wd, k), x.device)
+        N.check(lib.sx_conv2dmod_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), out.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                                     gw.data_ptr(), gy.data_ptr(), b, ci, co, h, wd, k, 1 if ctx.demod else 0, ctx.eps,
+                                     ws.data_ptr(), ws.numel(), N.stream_ptr()), "sx_conv2dmod_bwd")
+        return gx, gy, gw, None, None
 
 
 class RGBBlock(nn.Module):
@@ -172,6 +214,7 @@ class RGBBlock(nn.Module):
             Blur()
         ) if upsample else None
 
+    @torch.no_grad()     # inference op: only Conv2DMod has a native backward so far
     def forward(self, x, prev_rgb, istyle):
         b, c, h, w = x.shape
         style = linear(istyle, self.to_style.weight.detach(), self.to_style.bias.detach())
@@ -206,6 +249,7 @@ class GeneratorBlock(nn.Module):
         self.activation = leaky_relu()
         self.to_rgb = RGBBlock(latent_dim, filters, upsample_rgb, rgba)
 
+    @torch.no_grad()     # inference op: only Conv2DMod has a native backward so far
     def forward(self, x, prev_rgb, istyle, inoise):
         if exists(self.upsample):
             x = upsample2x(x)

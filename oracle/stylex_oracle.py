@@ -365,3 +365,21 @@ def encode_images(enc_params: Dict[str, Tensor], classify: Callable[[Tensor], Te
         lat.append(torch.cat((w, lg if use_old_architecture else torch.softmax(lg, dim=1)), dim=1))
         lgs.append(lg)
     return torch.cat(lat), torch.cat(lgs)
+
+
+# --------------------------------------------------------------------------------------
+# training-step slice: gradients of Conv2DMod
+# --------------------------------------------------------------------------------------
+def modconv_grads(x: Tensor, weight: Tensor, style: Tensor, grad_out: Tensor, demod: bool = True, eps: float = 1e-8,
+                  dtype: torch.dtype = torch.float64) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """What autograd derives for Conv2DMod.forward ST:647-667: (out, dL/dx, dL/dstyle, dL/dweight) for an upstream
+    gradient ``grad_out`` -- torch autograd through the literal restatement ``modconv`` (float64 by default, so the
+    oracle's own rounding is far below the 1e-4 parity tolerance)."""
+    with torch.enable_grad():
+        xs = x.detach().to(dtype).requires_grad_(True)
+        ws = weight.detach().to(dtype).requires_grad_(True)
+        ys = style.detach().to(dtype).requires_grad_(True)
+        out = modconv(xs, ws, ys, demod=demod, eps=eps)
+        gx, gy, gw = torch.autograd.grad(out, (xs, ys, ws), grad_out.to(dtype))
+    return out.detach(), gx, gy, gw
+

@@ -653,3 +653,93 @@ def test_stylex_container_checkpoint_on_device(dev, tmp_path):
     assert rgb.shape == (3, 3, 16, 16) and torch.isfinite(rgb).all()
     assert m2.D(rgb).shape == (3,)
     assert torch.equal(m2.GE(sx.styles_def_to_tensor([(lat, m2.G.num_layers)]), noise), rgb)   # GE == G after reset_parameter_averaging
+
+
+# ---- Conv2DMod backward ---------------------------------------------------------------
+def _rel(got, ref):
+    return float((got.double().cpu() - ref.double().cpu()).abs().max()) / max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", ["k3_demod", "k1_rgb", "k3_wide"])
+def test_conv2dmod_backward_matches_reference_autograd(dev, golden, case):
+    """sx_conv2dmod_bwd through torch.autograd against the gradients the UNMODIFIED reference module produced."""
+    z = golden("conv2dmod_grad.npz")
+    b, ci, co, hw, k, demod = (int(v) for v in z[f"{case}.cfg"])
+    t = {key: torch.from_numpy(z[f"{case}.{key}"]).to(dev) for key in ("x", "y", "w", "go", "out", "gx", "gy", "gw")}
+    conv = sx.Conv2DMod(ci, co, k, demod=bool(demod)).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(t["w"])
+    before = _native.launch_count()
+    with torch.enable_grad():
+        xs, ys = t["x"].clone().requires_grad_(True), t["y"].clone().requires_grad_(True)
+        out = conv(xs, ys)
+        gx, gy, gw = torch.autograd.grad(out, (xs, ys, conv.weight), t["go"])
+    assert _native.launch_count() - before >= 10                       # forward + backward kernels, all native
+    assert _rel(out, t["out"]) <= FP32_TOL
+    assert _rel(gx, t["gx"]) <= FP32_TOL
+    assert _rel(gy, t["gy"]) <= FP32_TOL
+    assert _rel(gw, t["gw"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("b,ci,co,hw,k,demod", [(4, 64, 32, 32, 3, True), (3, 128, 3, 16, 1, False), (2, 20, 36, 12, 3, True),
+                                                (1, 512, 512, 4, 3, True)])
+def test_conv2dmod_backward_matches_oracle_fp64(dev, b, ci, co, hw, k, demod):
+    """generator-sized and ragged shapes against torch autograd through the oracle's literal restatement in float64;
+    .backward() accumulates into .grad like any autograd op; deterministic (fixed-order split-K)."""
+    g = torch.Generator().manual_seed(b * 1000 + ci)
+    x = torch.randn(b, ci, hw, hw, generator=g)
+    y = torch.randn(b, ci, generator=g) * 0.5
+    w = torch.randn(co, ci, k, k, generator=g) * (2.0 / (ci * k * k)) ** 0.5
+    go = torch.randn(b, co, hw, hw, generator=g)
+    out_ref, gx_ref, gy_ref, gw_ref = O.modconv_grads(x, w, y, go, demod=demod)
+    conv = sx.Conv2DMod(ci, co, k, demod=demod).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_(w)
+    res = []
+    for _ in range(2):
+        conv.weight.grad = None
+        with torch.enable_grad():
+            xs, ys = x.to(dev).requires_grad_(True), y.to(dev).requires_grad_(True)
+            out = conv(xs, ys)
+            (out * go.to(dev)).sum().backward()
+        res.append((xs.grad.clone(), ys.grad.clone(), conv.weight.grad.clone()))
+    assert _rel(out.detach(), out_ref) <= FP32_TOL
+    assert _rel(res[0][0], gx_ref) <= FP32_TOL
+    assert _rel(res[0][1], gy_ref) <= FP32_TOL
+    assert _rel(res[0][2], gw_ref) <= FP32_TOL
+    for a, c in zip(res[0], res[1]):
+        assert torch.equal(a, c)                                       # bit-reproducible
+
+
+def test_conv2dmod_backward_properties(dev):
+    """size-independent properties: linear in the upstream gradient; a zero upstream gradient gives exact zeros; the
+    bf16 (inference) module and torch.no_grad() record no graph; an empty batch gives a zero weight gradient."""
+    g = torch.Generator().manual_seed(9)
+    b, ci, co, hw = 2, 32, 32, 16
+    x = torch.randn(b, ci, hw, hw, generator=g).to(dev)
+    y = (torch.randn(b, ci, generator=g) * 0.5).to(dev)
+    conv = sx.Conv2DMod(ci, co, 3).to(dev)
+    g1 = torch.randn(b, co, hw, hw, generator=g).to(dev)
+    g2 = torch.randn(b, co, hw, hw, generator=g).to(dev)
+
+    def grads(go):
+        with torch.enable_grad():
+            xs, ys = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            return torch.autograd.grad(conv(xs, ys), (xs, ys, conv.weight), go)
+
+    a, c, both = grads(g1), grads(g2), grads(2.0 * g1 - 0.5 * g2)
+    for ga, gc, gb in zip(a, c, both):
+        assert _rel(gb, 2.0 * ga - 0.5 * gc) <= FP32_TOL
+    for gz in grads(torch.zeros_like(g1)):
+        assert float(gz.abs().max()) == 0.0
+    with torch.no_grad():
+        assert not conv(x, y).requires_grad
+    conv.precision = "bf16"
+    with torch.enable_grad():
+        assert not conv(x.clone().requires_grad_(True), y).requires_grad
+    conv.precision = "fp32"
+    lib = _native.lib()
+    gw = torch.ones(co, ci, 3, 3, device=dev)
+    _native.check(lib.sx_conv2dmod_bwd(0, 0, 0, 0, 0, 0, gw.data_ptr(), 0, 0, ci, co, hw, hw, 3, 1, 1e-8, 0, 0, _native.stream_ptr()),
+                  "sx_conv2dmod_bwd")
+    assert float(gw.abs().max()) == 0.0
