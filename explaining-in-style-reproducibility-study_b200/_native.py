@@ -50,6 +50,11 @@ SIGNATURES = {
     "sx_noise_lrelu": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "sx_rgb_add_upsample_blur": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     "sx_linear_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "sx_linear_bwd": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
+    "sx_noise_lrelu_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "sx_noise_lrelu_bwd": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "sx_upsample2x_bilinear_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sx_blur3x3_reflect_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sx_resize_aa_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),
                                        POINTER(c_float), c_void_p]),
     "sx_resize_aa_normalize_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),

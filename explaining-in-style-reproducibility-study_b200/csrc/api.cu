@@ -6,6 +6,7 @@
 #include "attfind.cuh"
 #include "bandwidth.cuh"
 #include "common.cuh"
+#include "bwd_ops.cuh"
 #include "conv_bwd.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
@@ -283,6 +284,67 @@ int sx_linear_fwd(const float* x, const float* weight, const float* bias, float*
   return SX_OK;
 }
 
+
+// ---- backward of the bandwidth ops (bwd_ops.cuh) ---------------------------------------------------------------------
+int sx_linear_bwd(const float* x, const float* weight, const float* grad_out, float* grad_x, float* grad_weight, float* grad_bias,
+                  int B, int in_f, int out_f, sx_stream_t stream) {
+  SX_REQUIRE(B >= 0 && in_f >= 1 && out_f >= 1, "bad shape");
+  SX_REQUIRE(grad_weight, "null argument");
+  SX_REQUIRE(B == 0 || (x && weight && grad_out && grad_x), "null argument");
+  cudaStream_t st = S(stream);
+  linear_bwd_w_kernel<<<ew_grid((long long)out_f * in_f, 256), 256, 0, st>>>(grad_out, x, grad_weight, grad_bias, B, in_f, out_f);
+  SX_CHECK_LAUNCH();
+  if (B == 0) return SX_OK;
+  linear_bwd_x_kernel<<<ew_grid((long long)B * in_f, 256), 256, 0, st>>>(grad_out, weight, grad_x, B, in_f, out_f);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+size_t sx_noise_lrelu_bwd_workspace_bytes(int B, int C) { return B < 0 || C < 0 ? 0 : align_up((size_t)2 * B * C * 4, 256); }
+
+int sx_noise_lrelu_bwd(const float* out, const float* grad_out, const float* inoise, float* grad_x, float* grad_noise_w,
+                       float* grad_noise_b, int B, int C, int H, int W, int noise_batch, int noise_size, void* workspace,
+                       size_t ws_bytes, sx_stream_t stream) {
+  SX_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1, "bad shape");
+  SX_REQUIRE(grad_noise_w && grad_noise_b, "null argument");
+  cudaStream_t st = S(stream);
+  if (B == 0) {
+    SX_CUDA(cudaMemsetAsync(grad_noise_w, 0, (size_t)C * 4, st));
+    SX_CUDA(cudaMemsetAsync(grad_noise_b, 0, (size_t)C * 4, st));
+    return SX_OK;
+  }
+  SX_REQUIRE(out && grad_out && inoise && grad_x && workspace, "null argument");
+  SX_REQUIRE(noise_batch == 1 || noise_batch == B, "noise batch %d must be 1 or B=%d", noise_batch, B);
+  SX_REQUIRE(H <= noise_size && W <= noise_size, "noise map %d smaller than the activation %dx%d", noise_size, H, W);
+  SX_REQUIRE(ws_bytes >= sx_noise_lrelu_bwd_workspace_bytes(B, C), "workspace too small");
+  float* pw = reinterpret_cast<float*>(workspace);
+  float* pb = pw + (size_t)B * C;
+  noise_lrelu_bwd_kernel<<<(unsigned)((long long)B * C), 256, 0, st>>>(out, grad_out, inoise, grad_x, pw, pb, C, H, W, noise_batch, noise_size);
+  SX_CHECK_LAUNCH();
+  noise_param_reduce_kernel<<<(C + 127) / 128, 128, 0, st>>>(pw, pb, grad_noise_w, grad_noise_b, B, C);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+int sx_upsample2x_bilinear_bwd(const float* grad_out, float* grad_x, int B, int C, int H, int W, sx_stream_t stream) {
+  SX_REQUIRE(B >= 0 && C >= 0 && H >= 1 && W >= 1, "bad shape");
+  const long long planes = (long long)B * C;
+  if (planes == 0) return SX_OK;
+  SX_REQUIRE(grad_out && grad_x, "null argument");
+  upsample2x_bwd_nchw_kernel<<<ew_grid(planes * H * W, 256), 256, 0, S(stream)>>>(grad_out, grad_x, planes, H, W);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
+int sx_blur3x3_reflect_bwd(const float* grad_out, float* grad_x, int B, int C, int H, int W, sx_stream_t stream) {
+  SX_REQUIRE(B >= 0 && C >= 0 && H >= 2 && W >= 2, "blur with reflect border needs H, W >= 2");
+  const long long planes = (long long)B * C;
+  if (planes == 0) return SX_OK;
+  SX_REQUIRE(grad_out && grad_x, "null argument");
+  blur_bwd_nchw_kernel<<<ew_grid(planes * H * W, 256), 256, 0, S(stream)>>>(grad_out, grad_x, planes, H, W);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
 
 int sx_resize_aa_normalize(const float* in, void* out, int out_bf16, int B, int IH, int IW, int OH, int OW, int normalize,
                            const float* mean3, const float* std3, sx_stream_t stream) {

@@ -14,8 +14,10 @@ Two levels:
 * plan level (``Generator.forward`` and the AttFind sweep): the whole synthesis network runs inside
   the library on NHWC activations with fused epilogues (``GeneratorPlan``) -- this is the fast path.
 
-Inference only: the forwards do not record autograd graphs (the training step is a later row of
-SURVEY.md section 8f).
+Autograd (first slice): at module level every op is a ``torch.autograd.Function`` whose
+forward AND first-order backward are native kernels (``csrc/conv_bwd.cuh``, ``csrc/bwd_ops.cuh``), fp32, deterministic.
+``Generator.forward`` takes that path when gradients are being recorded; under ``torch.no_grad()`` (AttFind, rendering)
+it runs the fused plan, which records nothing.  Not twice differentiable (no path-length / gradient penalty yet).
 """
 from __future__ import annotations
 
@@ -69,6 +71,152 @@ def _noise_arg(inoise: torch.Tensor):
 # ---------------------------------------------------------------------------------------------
 # L1 ops
 # ---------------------------------------------------------------------------------------------
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _blur_fwd(x):
+    x = N.f32c(x)
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    N.check(N.lib().sx_blur3x3_reflect(x.data_ptr(), out.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_blur3x3_reflect")
+    return out
+
+
+def _blur_bwd(g):
+    g = N.f32c(g)
+    b, c, h, w = g.shape
+    gx = torch.empty_like(g)
+    N.check(N.lib().sx_blur3x3_reflect_bwd(g.data_ptr(), gx.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_blur3x3_reflect_bwd")
+    return gx
+
+
+def _up_fwd(x):
+    x = N.f32c(x)
+    b, c, h, w = x.shape
+    out = torch.empty(b, c, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
+    N.check(N.lib().sx_upsample2x_bilinear(x.data_ptr(), out.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_upsample2x_bilinear")
+    return out
+
+
+def _up_bwd(g):
+    g = N.f32c(g)
+    b, c, h2, w2 = g.shape
+    gx = torch.empty(b, c, h2 // 2, w2 // 2, device=g.device, dtype=torch.float32)
+    N.check(N.lib().sx_upsample2x_bilinear_bwd(g.data_ptr(), gx.data_ptr(), b, c, h2 // 2, w2 // 2, N.stream_ptr()),
+            "sx_upsample2x_bilinear_bwd")
+    return gx
+
+
+class BlurFunction(torch.autograd.Function):
+    """Blur.forward ST:144-153 / its adjoint (reflected border taps fold back inside)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _blur_fwd(x.detach())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        return _blur_bwd(g)
+
+
+class Upsample2xFunction(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) ST:679 / its adjoint."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _up_fwd(x.detach())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        return _up_bwd(g)
+
+
+class LinearFunction(torch.autograd.Function):
+    """nn.Linear (to_style1/2, RGBBlock.to_style) forward / backward on the native kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xd, wd = N.f32c(x.detach()), N.f32c(weight.detach())
+        bd = None if bias is None else N.f32c(bias.detach())
+        out = torch.empty(xd.shape[0], wd.shape[0], device=xd.device, dtype=torch.float32)
+        N.check(N.lib().sx_linear_fwd(xd.data_ptr(), wd.data_ptr(), N.ptr(bd), out.data_ptr(), xd.shape[0], xd.shape[1],
+                                      wd.shape[0], N.stream_ptr()), "sx_linear_fwd")
+        ctx.save_for_backward(xd, wd)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = N.f32c(g)
+        gx, gw = torch.empty_like(x), torch.empty_like(w)
+        gb = torch.empty(w.shape[0], device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        N.check(N.lib().sx_linear_bwd(x.data_ptr(), w.data_ptr(), g.data_ptr(), gx.data_ptr(), gw.data_ptr(), N.ptr(gb),
+                                      x.shape[0], x.shape[1], w.shape[0], N.stream_ptr()), "sx_linear_bwd")
+        return gx, gw, gb
+
+
+class NoiseLReLUFunction(torch.autograd.Function):
+    """leaky_relu_0.2(x + to_noise(inoise[:, :H, :W]).permute(0,3,2,1)) ST:696-698,705,714 and its backward: grad_x and
+    the gradients of the to_noise Linear(1, C) (the noise map itself is data)."""
+
+    @staticmethod
+    def forward(ctx, x, inoise, nw, nbias):
+        xd = N.f32c(x.detach())
+        nz, nb, ns = _noise_arg(inoise)
+        b, c, h, w = xd.shape
+        out = torch.empty_like(xd)
+        nwd, nbd = N.f32c(nw.detach()), N.f32c(nbias.detach())
+        N.check(N.lib().sx_noise_lrelu(xd.data_ptr(), nz.data_ptr(), nwd.data_ptr(), nbd.data_ptr(), out.data_ptr(), b, c, h, w,
+                                       nb, ns, N.stream_ptr()), "sx_noise_lrelu")
+        ctx.save_for_backward(out, nz)
+        ctx.noise = (nb, ns)
+        ctx.w_shape = tuple(nw.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        out, nz = ctx.saved_tensors
+        nb, ns = ctx.noise
+        g = N.f32c(g)
+        b, c, h, w = out.shape
+        lib = N.lib()
+        gx = torch.empty_like(out)
+        gnw = torch.empty(c, device=out.device, dtype=torch.float32)
+        gnb = torch.empty_like(gnw)
+        ws = _op_ws.get(lib.sx_noise_lrelu_bwd_workspace_bytes(b, c), out.device)
+        N.check(lib.sx_noise_lrelu_bwd(out.data_ptr(), g.data_ptr(), nz.data_ptr(), gx.data_ptr(), gnw.data_ptr(), gnb.data_ptr(),
+                                       b, c, h, w, nb, ns, ws.data_ptr(), ws.numel(), N.stream_ptr()), "sx_noise_lrelu_bwd")
+        return gx, None, gnw.reshape(ctx.w_shape), gnb
+
+
+class RGBTailFunction(torch.autograd.Function):
+    """RGBBlock tail ST:623-627: out = blur(upsample2x(rgb + prev)) (or rgb + prev for the last block), one fused native
+    kernel; backward = blur adjoint -> upsample adjoint, and the same gradient flows to both summands."""
+
+    @staticmethod
+    def forward(ctx, rgb, prev, up):
+        x = N.f32c(rgb.detach())
+        pv = None if prev is None else N.f32c(prev.detach())
+        b, c, h, w = x.shape
+        out = torch.empty(b, c, h * (2 if up else 1), w * (2 if up else 1), device=x.device, dtype=torch.float32)
+        N.check(N.lib().sx_rgb_add_upsample_blur(x.data_ptr(), N.ptr(pv), out.data_ptr(), b, c, h, w, 1 if up else 0,
+                                                 N.stream_ptr()), "sx_rgb_add_upsample_blur")
+        ctx.up, ctx.has_prev = up, prev is not None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        gs = _up_bwd(_blur_bwd(g)) if ctx.up else N.f32c(g)
+        return gs, (gs if ctx.has_prev else None), None
+
+
 class Blur(nn.Module):
     def __init__(self):
         super().__init__()
@@ -77,47 +225,27 @@ class Blur(nn.Module):
     def forward(self, x):
         N.require_cuda(x)
         N.device_check()
-        x = N.f32c(x)
-        b, c, h, w = x.shape
-        out = torch.empty_like(x)
-        N.check(N.lib().sx_blur3x3_reflect(x.data_ptr(), out.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_blur3x3_reflect")
-        return out
+        return BlurFunction.apply(x)
 
 
 def upsample2x(x: torch.Tensor) -> torch.Tensor:
     """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) on the native kernel."""
     N.require_cuda(x)
     N.device_check()
-    x = N.f32c(x)
-    b, c, h, w = x.shape
-    out = torch.empty(b, c, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
-    N.check(N.lib().sx_upsample2x_bilinear(x.data_ptr(), out.data_ptr(), b, c, h, w, N.stream_ptr()), "sx_upsample2x_bilinear")
-    return out
+    return Upsample2xFunction.apply(x)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     N.require_cuda(x, weight, bias)
     N.device_check()
-    x, weight = N.f32c(x), N.f32c(weight)
-    bias = None if bias is None else N.f32c(bias)
-    out = torch.empty(x.shape[0], weight.shape[0], device=x.device, dtype=torch.float32)
-    N.check(N.lib().sx_linear_fwd(x.data_ptr(), weight.data_ptr(), N.ptr(bias), out.data_ptr(), x.shape[0], x.shape[1],
-                                  weight.shape[0], N.stream_ptr()), "sx_linear_fwd")
-    return out
+    return LinearFunction.apply(x, weight, bias)
 
 
 def noise_lrelu(x: torch.Tensor, inoise: torch.Tensor, to_noise: nn.Linear) -> torch.Tensor:
     """leaky_relu_0.2(x + to_noise(inoise[:, :H, :W]).permute(0,3,2,1)) -- reference :696-698,705."""
     N.require_cuda(x, inoise)
     N.device_check()
-    x = N.f32c(x)
-    nz, nb, ns = _noise_arg(inoise)
-    b, c, h, w = x.shape
-    out = torch.empty_like(x)
-    nw, nbias = N.f32c(to_noise.weight.detach()), N.f32c(to_noise.bias.detach())
-    N.check(N.lib().sx_noise_lrelu(x.data_ptr(), nz.data_ptr(), nw.data_ptr(), nbias.data_ptr(), out.data_ptr(), b, c, h, w,
-                                   nb, ns, N.stream_ptr()), "sx_noise_lrelu")
-    return out
+    return NoiseLReLUFunction.apply(x, inoise, to_noise.weight, to_noise.bias)
 
 
 class Conv2DMod(nn.Module):
@@ -214,17 +342,10 @@ class RGBBlock(nn.Module):
             Blur()
         ) if upsample else None
 
-    @torch.no_grad()     # inference op: only Conv2DMod has a native backward so far
     def forward(self, x, prev_rgb, istyle):
-        b, c, h, w = x.shape
-        style = linear(istyle, self.to_style.weight.detach(), self.to_style.bias.detach())
+        style = linear(istyle, self.to_style.weight, self.to_style.bias)
         x = self.conv(x, style)
-        prev = None if prev_rgb is None else N.f32c(prev_rgb)
-        up = exists(self.upsample)
-        out = torch.empty(b, x.shape[1], h * (2 if up else 1), w * (2 if up else 1), device=x.device, dtype=torch.float32)
-        N.check(N.lib().sx_rgb_add_upsample_blur(x.data_ptr(), N.ptr(prev), out.data_ptr(), b, x.shape[1], h, w,
-                                                 1 if up else 0, N.stream_ptr()), "sx_rgb_add_upsample_blur")
-        return out
+        return RGBTailFunction.apply(x, prev_rgb, exists(self.upsample))
 
 
 class GeneratorBlock(nn.Module):
@@ -249,14 +370,13 @@ class GeneratorBlock(nn.Module):
         self.activation = leaky_relu()
         self.to_rgb = RGBBlock(latent_dim, filters, upsample_rgb, rgba)
 
-    @torch.no_grad()     # inference op: only Conv2DMod has a native backward so far
     def forward(self, x, prev_rgb, istyle, inoise):
         if exists(self.upsample):
             x = upsample2x(x)
-        style1 = linear(istyle, self.to_style1.weight.detach(), self.to_style1.bias.detach())
+        style1 = linear(istyle, self.to_style1.weight, self.to_style1.bias)
         x = self.conv1(x, style1)
         x = noise_lrelu(x, inoise, self.to_noise1)
-        style2 = linear(istyle, self.to_style2.weight.detach(), self.to_style2.bias.detach())
+        style2 = linear(istyle, self.to_style2.weight, self.to_style2.bias)
         style_coords = torch.cat([style1, style2], dim=-1)
         x = self.conv2(x, style2)
         x = noise_lrelu(x, inoise, self.to_noise2)
@@ -427,11 +547,29 @@ class Generator(nn.Module):
 
     def forward(self, styles, input_noise, get_style_coords=False):
         """styles [B, L, latent], input_noise [B|1, S, S, 1] -> rgb [B,3,S,S] (, style_coords [B, S_total])."""
+        if _prec(self) == N.PREC_FP32 and _wants_grad(styles, *self.parameters()):
+            return self._forward_autograd(styles, input_noise, get_style_coords)
         plan = self.plan()
         styles_all = plan.styles(styles)
         rgb = plan.forward(styles_all, input_noise, precision=self.precision)
         if get_style_coords:
             return rgb, styles_all[:, :plan.S].clone()
+        return rgb
+
+    def _forward_autograd(self, styles, input_noise, get_style_coords=False):
+        """ST:794-825 op by op at module level: every op is an autograd Function over native kernels, so the graph torch
+        records gives d(rgb)/d(every generator parameter, styles).  ``initial_conv`` is a plain batch-invariant
+        convolution (ST:802,806) and goes through PyTorch like the encoder's convolutions."""
+        N.require_cuda(styles, input_noise)
+        batch_size = styles.shape[0]
+        x = self.initial_conv(self.initial_block).expand(batch_size, -1, -1, -1)
+        rgb = None
+        coords = []
+        for style, block in zip(styles.transpose(0, 1), self.blocks):
+            x, rgb, sc = block(x, rgb, style, input_noise)
+            coords.append(sc)
+        if get_style_coords:
+            return rgb, torch.cat(coords, dim=1)
         return rgb
 
     def forward_from_styles(self, styles_all, input_noise):

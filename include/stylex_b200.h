@@ -100,6 +100,25 @@ int sx_rgb_add_upsample_blur(const float* rgb, const float* prev, float* out, in
 int sx_linear_fwd(const float* x, const float* weight, const float* bias, float* out, int B, int in_features,
                   int out_features, sx_stream_t stream);
 
+/* ---- first-order backward of the ops above (training step).  All deterministic gathers. ---- */
+
+/* nn.Linear: grad_x[B,in] = g W, grad_weight[out,in] = g^T x, grad_bias[out] = sum_b g (grad_bias may be NULL). */
+int sx_linear_bwd(const float* x, const float* weight, const float* grad_out, float* grad_x, float* grad_weight,
+                  float* grad_bias, int B, int in_features, int out_features, sx_stream_t stream);
+
+/* noise + leaky-ReLU (sx_noise_lrelu): from the forward OUTPUT and grad_out -> grad_x[B,C,H,W] and the gradients of
+ * the to_noise Linear(1, C): grad_noise_w[C] = sum grad_x * inoise[b|0, x, y] (transposed, quirk Q1), grad_noise_b[C]. */
+size_t sx_noise_lrelu_bwd_workspace_bytes(int B, int C);
+int sx_noise_lrelu_bwd(const float* out, const float* grad_out, const float* inoise, float* grad_x, float* grad_noise_w,
+                       float* grad_noise_b, int B, int C, int H, int W, int noise_batch, int noise_size,
+                       void* workspace, size_t workspace_bytes, sx_stream_t stream);
+
+/* adjoint of sx_upsample2x_bilinear: grad_out[B,C,2H,2W] -> grad_x[B,C,H,W]. */
+int sx_upsample2x_bilinear_bwd(const float* grad_out, float* grad_x, int B, int C, int H, int W, sx_stream_t stream);
+
+/* adjoint of sx_blur3x3_reflect (reflected border taps fold back inside): same shape. */
+int sx_blur3x3_reflect_bwd(const float* grad_out, float* grad_x, int B, int C, int H, int W, sx_stream_t stream);
+
 /* The tensor branch of ResNet.classify_images' preprocessing (resnet_classifier.py:60-68) in one pass:
  * torchvision resize(images, [OH,OW]) (bilinear, antialias=True: ATen's _upsample_bilinear2d_aa arithmetic) ->
  * Normalize(mean, std) (optional) -> cast -> channels_last.  in [B,3,IH,IW] fp32 NCHW; out [B,OH,OW,3] fp32 or bf16,

@@ -383,3 +383,16 @@ def modconv_grads(x: Tensor, weight: Tensor, style: Tensor, grad_out: Tensor, de
         gx, gy, gw = torch.autograd.grad(out, (xs, ys, ws), grad_out.to(dtype))
     return out.detach(), gx, gy, gw
 
+
+def generator_grads(params: Dict[str, Tensor], styles: Tensor, input_noise: Tensor, grad_out: Tensor,
+                    dtype: torch.dtype = torch.float64) -> Tuple[Tensor, Dict[str, Tensor], Tensor]:
+    """What autograd derives for Generator.forward ST:794-825: (rgb, {parameter key: dL/dparam}, dL/dstyles) for an
+    upstream gradient ``grad_out`` on the image -- torch autograd through ``generator_forward`` above."""
+    with torch.enable_grad():
+        ps = {k: v.detach().to(dtype).requires_grad_(True) for k, v in params.items() if not k.endswith(".f")}
+        st = styles.detach().to(dtype).requires_grad_(True)
+        rgb = generator_forward(ps, st, input_noise.to(dtype))
+        keys = list(ps)
+        grads = torch.autograd.grad(rgb, [ps[k] for k in keys] + [st], grad_out.to(dtype), allow_unused=True)
+    return rgb.detach(), {k: g for k, g in zip(keys, grads[:-1])}, grads[-1]
+

@@ -743,3 +743,103 @@ def test_conv2dmod_backward_properties(dev):
     _native.check(lib.sx_conv2dmod_bwd(0, 0, 0, 0, 0, 0, gw.data_ptr(), 0, 0, ci, co, hw, hw, 3, 1, 1e-8, 0, 0, _native.stream_ptr()),
                   "sx_conv2dmod_bwd")
     assert float(gw.abs().max()) == 0.0
+
+
+def test_generator_backward_matches_reference_autograd(dev, golden):
+    """Generator.forward with gradients recorded (every op a native forward + native backward) against the gradients the
+    UNMODIFIED reference Generator produced under torch autograd: all 42 parameters and the styles."""
+    z = golden("generator_grad.npz")
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    sd = synthetic.make_generator_state(size, seed=31, network_capacity=cap)
+    G = g_module(sd, size, cap, dev).train()
+    b = z["go"].shape[0]
+    styles = synthetic.make_latents(b * G.num_layers, 32).reshape(b, G.num_layers, -1).to(dev)
+    noise = synthetic.make_noise(size, 31).to(dev)
+    go = torch.from_numpy(z["go"]).to(dev)
+    before = _native.launch_count()
+    with torch.enable_grad():
+        st = styles.clone().requires_grad_(True)
+        rgb = G(st, noise)
+        assert rgb.requires_grad
+        (rgb * go).sum().backward()
+    assert _native.launch_count() - before > 100
+    assert _rel(rgb.detach(), torch.from_numpy(z["rgb"])) <= FP32_TOL
+    # the same forward through the fused plan (no graph) agrees with the module-level autograd path
+    assert _rel(G(styles, noise), rgb.detach()) <= FP32_TOL
+    names = [k[2:] for k in z.files if k.startswith("g.")]
+    params = dict(G.named_parameters())
+    assert sorted(names) == sorted(params)
+    for n in names:
+        assert params[n].grad is not None, n
+        assert _rel(params[n].grad, torch.from_numpy(z["g." + n])) <= FP32_TOL, n
+    assert _rel(st.grad, torch.from_numpy(z["g_styles"])) <= FP32_TOL
+
+
+def test_generator_backward_64px_vs_oracle(dev):
+    """BASELINE-shaped 64px generator (capacity 16, 512-channel blocks): image-loss gradients against float64 autograd
+    through the oracle for a sample of parameters of every kind."""
+    size = 64
+    sd = synthetic.make_generator_state(size, seed=42)
+    G = g_module(sd, size, 16, dev).train()
+    b = 2
+    lat = synthetic.make_latents(b, 5)
+    styles = O.styles_def_to_tensor([(lat, G.num_layers)])
+    noise = synthetic.make_noise(size, 42)
+    go = torch.randn(b, 3, size, size, generator=torch.Generator().manual_seed(1))
+    _, ref, ref_st = O.generator_grads(sd, styles, noise, go, dtype=torch.float64)
+    with torch.enable_grad():
+        st = styles.to(dev).requires_grad_(True)
+        rgb = G(st, noise.to(dev))
+        (rgb * go.to(dev)).sum().backward()
+    params = dict(G.named_parameters())
+    for n in ("initial_block", "initial_conv.weight", "blocks.0.conv1.weight", "blocks.0.to_style1.weight", "blocks.1.to_noise1.weight",
+              "blocks.2.conv2.weight", "blocks.3.to_rgb.conv.weight", "blocks.3.to_rgb.to_style.bias", "blocks.4.conv1.weight",
+              "blocks.4.to_noise2.bias", "blocks.4.to_style2.weight"):
+        assert _rel(params[n].grad, ref[n]) <= 2e-4, n          # fp32 sums over up to 64*64*2 pixels and 512 channels
+    assert _rel(st.grad, ref_st) <= 2e-4
+
+
+def test_bandwidth_op_adjoints(dev):
+    """<op(x), g> == <x, op_bwd(g)> for the linear maps (upsample, blur) on ragged sizes, and the closed forms of the
+    noise / linear backward against torch autograd of the same expressions."""
+    g = torch.Generator().manual_seed(3)
+    for (b, c, h, w) in [(2, 3, 2, 2), (1, 5, 7, 4), (3, 4, 16, 16)]:
+        x = torch.randn(b, c, h, w, generator=g, dtype=torch.float32).to(dev)
+        gu = torch.randn(b, c, 2 * h, 2 * w, generator=g).to(dev)
+        gb = torch.randn(b, c, h, w, generator=g).to(dev)
+        with torch.enable_grad():
+            xs = x.clone().requires_grad_(True)
+            (gxu,) = torch.autograd.grad(sx.modules.upsample2x(xs), xs, gu)
+            xs2 = x.clone().requires_grad_(True)
+            (gxb,) = torch.autograd.grad(sx.Blur().to(dev)(xs2), xs2, gb)
+            xr = x.clone().requires_grad_(True)
+            ref_u = torch.nn.functional.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+            (ru,) = torch.autograd.grad(ref_u, xr, gu)
+            xr2 = x.cpu().clone().requires_grad_(True)
+            (rb,) = torch.autograd.grad(O.blur3x3_reflect(xr2), xr2, gb.cpu())
+        assert _rel(gxu, ru) <= 1e-5 and _rel(gxb, rb) <= 1e-5
+    # linear
+    x = torch.randn(5, 514, generator=g).to(dev)
+    lin = torch.nn.Linear(514, 48).to(dev)
+    go = torch.randn(5, 48, generator=g).to(dev)
+    with torch.enable_grad():
+        xs = x.clone().requires_grad_(True)
+        got = torch.autograd.grad(sx.modules.linear(xs, lin.weight, lin.bias), (xs, lin.weight, lin.bias), go)
+        xr = x.clone().requires_grad_(True)
+        ref = torch.autograd.grad(torch.nn.functional.linear(xr, lin.weight, lin.bias), (xr, lin.weight, lin.bias), go)
+    for a, r in zip(got, ref):
+        assert _rel(a, r) <= 1e-5
+    # noise + leaky-ReLU (transposed noise, quirk Q1), per-sample and broadcast noise maps
+    for nb in (1, 3):
+        xin = torch.randn(3, 6, 8, 8, generator=g).to(dev)
+        inoise = torch.rand(nb, 16, 16, 1, generator=g).to(dev)
+        tn = torch.nn.Linear(1, 6).to(dev)
+        go = torch.randn(3, 6, 8, 8, generator=g).to(dev)
+        with torch.enable_grad():
+            xs = xin.clone().requires_grad_(True)
+            got = torch.autograd.grad(sx.modules.noise_lrelu(xs, inoise, tn), (xs, tn.weight, tn.bias), go)
+            xr = xin.clone().requires_grad_(True)
+            nz = tn(inoise[:, :8, :8, :]).permute((0, 3, 2, 1))
+            ref = torch.autograd.grad(torch.nn.functional.leaky_relu(xr + nz, 0.2), (xr, tn.weight, tn.bias), go)
+        for a, r in zip(got, ref):
+            assert a.shape == r.shape and _rel(a, r) <= 1e-5

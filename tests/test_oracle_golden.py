@@ -172,3 +172,23 @@ def test_conv2dmod_gradients_match_reference_autograd(golden, case):
     # fp32 evaluation of the same restatement agrees too (the reference ran in fp32)
     _, gx32, gy32, gw32 = O.modconv_grads(t["x"], t["w"], t["y"], t["go"], demod=bool(demod), dtype=torch.float32)
     assert float((gw32 - t["gw"]).abs().max()) <= 2e-5 * float(t["gw"].abs().max())
+
+
+def test_generator_gradients_match_reference_autograd(golden):
+    z = golden("generator_grad.npz")
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    sd = synthetic.make_generator_state(size, seed=31, network_capacity=cap)
+    L = len(O.generator_layout(sd))
+    b = z["go"].shape[0]
+    styles = synthetic.make_latents(b * L, 32).reshape(b, L, -1)
+    noise = synthetic.make_noise(size, 31)
+    fp = np.array([float(sd["blocks.0.conv1.weight"].double().sum()), float(styles.double().sum()), float(noise.double().sum())])
+    assert np.allclose(fp, z["fp"], rtol=1e-9, atol=1e-6), "torch CPU RNG drifted: seeded inputs differ"
+    rgb, grads, gst = O.generator_grads(sd, styles, noise, torch.from_numpy(z["go"]))
+    assert np.abs(rgb.float().numpy() - z["rgb"]).max() <= 5e-6
+    names = [k[2:] for k in z.files if k.startswith("g.")]
+    assert sorted(names) == sorted(grads)
+    for n in names:
+        ref = z["g." + n]
+        assert np.abs(grads[n].float().numpy() - ref).max() <= 5e-5 * max(1.0, np.abs(ref).max()), n
+    assert np.abs(gst.float().numpy() - z["g_styles"]).max() <= 5e-5 * max(1.0, np.abs(z["g_styles"]).max())
