@@ -843,3 +843,26 @@ def test_bandwidth_op_adjoints(dev):
             ref = torch.autograd.grad(torch.nn.functional.leaky_relu(xr + nz, 0.2), (xr, tn.weight, tn.bias), go)
         for a, r in zip(got, ref):
             assert a.shape == r.shape and _rel(a, r) <= 1e-5
+
+
+@pytest.mark.parametrize("tag,enc,seed", [("dis", False, 22), ("enc", True, 21)])
+def test_discriminator_backward_matches_reference_autograd(dev, golden, tag, enc, seed):
+    """DiscriminatorE under autograd (cuDNN convolutions + the native blur forward / adjoint kernels) against the executed
+    reference: input-image gradient (what the gradient penalty and the encoder path differentiate) and parameter gradients."""
+    z = golden("discriminator_grad.npz")
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    m = sx.DiscriminatorE(size, cap, encoder=enc)
+    m.load_state_dict(synthetic.make_discriminator_state(size, seed=seed, network_capacity=cap, encoder=enc), strict=False)
+    m = m.to(dev).train()
+    before = _native.launch_count()
+    with torch.enable_grad():
+        x = torch.from_numpy(z["images"]).to(dev).requires_grad_(True)
+        out = m(x)
+        (out * torch.from_numpy(z[f"{tag}.go"]).to(dev)).sum().backward()
+    assert _native.launch_count() - before == 6                         # 3 blurs forward + 3 adjoints
+    assert _rel(out.detach(), torch.from_numpy(z[f"{tag}.out"])) <= FP32_TOL
+    assert _rel(x.grad, torch.from_numpy(z[f"{tag}.g_images"])) <= FP32_TOL
+    params = dict(m.named_parameters())
+    keys = [k[len(tag) + 3:] for k in z.files if k.startswith(tag + ".g.")]
+    for k in keys:
+        assert _rel(params[k].grad, torch.from_numpy(z[f"{tag}.g.{k}"])) <= FP32_TOL, k

@@ -192,3 +192,22 @@ def test_generator_gradients_match_reference_autograd(golden):
         ref = z["g." + n]
         assert np.abs(grads[n].float().numpy() - ref).max() <= 5e-5 * max(1.0, np.abs(ref).max()), n
     assert np.abs(gst.float().numpy() - z["g_styles"]).max() <= 5e-5 * max(1.0, np.abs(z["g_styles"]).max())
+
+
+@pytest.mark.parametrize("tag,enc,seed", [("dis", False, 22), ("enc", True, 21)])
+def test_discriminator_gradients_match_reference_autograd(golden, tag, enc, seed):
+    z = golden("discriminator_grad.npz")
+    size, cap = int(z["image_size"]), int(z["network_capacity"])
+    sd = synthetic.make_discriminator_state(size, seed=seed, network_capacity=cap, encoder=enc)
+    with torch.enable_grad():
+        ps = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        x = torch.from_numpy(z["images"]).requires_grad_(True)
+        out = O.discriminator_forward(ps, x)
+        keys = [k[len(tag) + 3:] for k in z.files if k.startswith(tag + ".g.")]
+        grads = torch.autograd.grad(out, [x] + [ps[k] for k in keys], torch.from_numpy(z[f"{tag}.go"]))
+    assert np.abs(out.detach().numpy() - z[f"{tag}.out"]).max() <= 5e-6
+    assert np.abs(grads[0].numpy() - z[f"{tag}.g_images"]).max() <= 2e-5 * max(1.0, np.abs(z[f"{tag}.g_images"]).max())
+    assert len(keys) >= 10
+    for k, g in zip(keys, grads[1:]):
+        ref = z[f"{tag}.g.{k}"]
+        assert np.abs(g.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), k
