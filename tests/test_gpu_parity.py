@@ -866,3 +866,25 @@ def test_discriminator_backward_matches_reference_autograd(dev, golden, tag, enc
     keys = [k[len(tag) + 3:] for k in z.files if k.startswith(tag + ".g.")]
     for k in keys:
         assert _rel(params[k].grad, torch.from_numpy(z[f"{tag}.g.{k}"])) <= FP32_TOL, k
+
+
+@pytest.mark.parametrize("size", [256, 300, 64, 224])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_resize_s2d_separable_equals_direct(dev, size, dtype):
+    """the separable (shared-memory, two-pass) space-to-depth preprocessing kernel performs the direct kernel's fp32
+    operations in the same order: bit-identical outputs for down-scaling, up-scaling and identity resizes."""
+    from stylex_b200.classifiers import space_to_depth_input
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 224 * 224, 2)).to(dev)
+    clf = sx.make_classifier("resnet", model, size)
+    clf.to(dev).set_compute(dtype, channels_last=True)
+    g = torch.Generator().manual_seed(size)
+    x = (torch.rand(5, 3, size, size, generator=g) * 4 - 1.5).to(dev)
+    sep = clf._native_pre(x, s2d=True)
+    os.environ["SX_RESIZE_DIRECT"] = "1"
+    try:
+        direct = clf._native_pre(x, s2d=True)
+    finally:
+        del os.environ["SX_RESIZE_DIRECT"]
+    assert sep.shape == (5, 16, 115, 115)
+    assert torch.equal(sep, direct)
+    assert torch.equal(sep, space_to_depth_input(clf._native_pre(x)))
