@@ -43,8 +43,8 @@ SIGNATURES = {
     "sx_launch_count": (c_ulonglong, []),
     "sx_conv2dmod_workspace_bytes": (c_size_t, [c_int] * 7),
     "sx_conv2dmod_fwd": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
-    "sx_conv2dmod_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
-    "sx_conv2dmod_bwd": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, c_void_p, c_size_t, c_void_p]),
+    "sx_conv2dmod_bwd_workspace_bytes": (c_size_t, [c_int] * 7),
+    "sx_conv2dmod_bwd": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "sx_upsample2x_bilinear": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sx_blur3x3_reflect": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sx_noise_lrelu": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),

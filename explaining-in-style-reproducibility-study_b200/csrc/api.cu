@@ -13,6 +13,7 @@
 #include "conv_tc_halo.cuh"
 #include "generator.cuh"
 #include "preprocess.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace sx;
 
@@ -121,17 +122,26 @@ int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, fl
                             H, W, k, ep, st);
 }
 
-// ---- Conv2DMod backward (first order) -- conv_bwd.cuh ---------------------------------------------------------
+// ---- Conv2DMod backward (first order) -- conv_bwd.cuh, wgrad_tc.cuh ------------------------------------------------
+// SX_PREC_FP32: FFMA implicit GEMMs (the <= 1e-4 parity mode).  SX_PREC_BF16: the two big contractions run on the tensor
+// cores where the kernels take the shape -- dgrad on the tcgen05 conv kernels with flipped / transposed weights, wgrad as a
+// tcgen05 GEMM over K = pixels (wgrad_tc.cuh) -- and on the FFMA kernels otherwise (k = 1, 4x4 maps, odd channel counts);
+// the small per-sample reductions stay fp32 in both modes.
 struct Conv2dModBwdWs {
-  size_t gz, xm, wT, wsq, dcoef, gdot, gm1, msq, partial, total;
-  int splits;
+  size_t gz, xm, wT, wsq, dcoef, gdot, gm1, msq, partial, gz_bf, wT_bf, gzp_bf, xmp_bf, total;
+  int splits, splits_tc;
+  bool dgrad_tc, wgrad_tc;
 };
-static Conv2dModBwdWs conv2dmod_bwd_ws(int B, int Ci, int Co, int H, int W, int k) {
+static Conv2dModBwdWs conv2dmod_bwd_ws(int B, int Ci, int Co, int H, int W, int k, int precision) {
   Conv2dModBwdWs w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t HW = (size_t)H * W;
+  // SX_BWD_NO_TC_DGRAD / SX_BWD_NO_TC_WGRAD: keep one contraction on the FFMA kernels (A/B measurements, bisecting)
+  w.dgrad_tc = precision == SX_PREC_BF16 && tc::tc_shape_supported(Co, Ci, H, W, k) && !getenv("SX_BWD_NO_TC_DGRAD");
+  w.wgrad_tc = precision == SX_PREC_BF16 && tc::wgrad_tc_supported(Ci, Co, H, W, k) && !getenv("SX_BWD_NO_TC_WGRAD");
   w.splits = wgrad_splits(B, Ci, Co, H, W, k);
+  w.splits_tc = w.wgrad_tc ? tc::wgrad_tc_splits(B, Ci, Co, H, W, k) : 0;
   w.gz = take((size_t)B * HW * Co * 4);
   w.xm = take((size_t)B * HW * Ci * 4);
   w.wT = take((size_t)k * k * Ci * Co * 4);
@@ -140,21 +150,31 @@ static Conv2dModBwdWs conv2dmod_bwd_ws(int B, int Ci, int Co, int H, int W, int 
   w.gdot = take((size_t)B * Co * 4);
   w.gm1 = take((size_t)B * Ci * 4);
   w.msq = take((size_t)B * Ci * 4);
-  w.partial = take((size_t)w.splits * k * k * Co * Ci * 4);
+  const int smax = w.splits > w.splits_tc ? w.splits : w.splits_tc;
+  w.partial = take((size_t)smax * k * k * Co * Ci * 4);
+  if (w.dgrad_tc) {
+    w.gz_bf = take((size_t)B * HW * Co * 2);
+    w.wT_bf = take((size_t)k * k * Ci * Co * 2);
+  }
+  if (w.wgrad_tc) {
+    w.gzp_bf = take((size_t)B * HW * Co * 2);
+    w.xmp_bf = take((size_t)k * B * HW * Ci * 2);   // k copies shifted along x (wgrad_tc.cuh)
+  }
   w.total = off;
   return w;
 }
 
-size_t sx_conv2dmod_bwd_workspace_bytes(int B, int Ci, int Co, int H, int W, int k) {
+size_t sx_conv2dmod_bwd_workspace_bytes(int B, int Ci, int Co, int H, int W, int k, int precision) {
   if (B < 1 || Ci < 1 || Co < 1 || H < 1 || W < 1 || k < 1) return 0;
-  return conv2dmod_bwd_ws(B, Ci, Co, H, W, k).total;
+  return conv2dmod_bwd_ws(B, Ci, Co, H, W, k, precision).total;
 }
 
 int sx_conv2dmod_bwd(const float* x, const float* weight, const float* style, const float* out, const float* grad_out,
                      float* grad_x, float* grad_weight, float* grad_style, int B, int Ci, int Co, int H, int W, int k,
-                     int demod, float eps, void* workspace, size_t ws_bytes, sx_stream_t stream) {
+                     int demod, float eps, int precision, void* workspace, size_t ws_bytes, sx_stream_t stream) {
   SX_REQUIRE(B >= 0 && Ci >= 1 && Co >= 1 && H >= 1 && W >= 1, "bad shape B=%d Ci=%d Co=%d H=%d W=%d", B, Ci, Co, H, W);
   SX_REQUIRE(k == 1 || k == 3, "kernel size %d not supported (1 or 3)", k);
+  SX_REQUIRE(precision == SX_PREC_FP32 || precision == SX_PREC_BF16, "precision=%d", precision);
   SX_REQUIRE(grad_weight, "null argument");
   cudaStream_t st = S(stream);
   if (B == 0) {   // empty batch: the weight gradient is zero, nothing else to write
@@ -164,17 +184,17 @@ int sx_conv2dmod_bwd(const float* x, const float* weight, const float* style, co
   SX_REQUIRE(x && weight && style && grad_out && grad_x && grad_style && workspace, "null argument");
   SX_REQUIRE(!demod || out, "demod backward needs the forward output");
   SX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-  const Conv2dModBwdWs L = conv2dmod_bwd_ws(B, Ci, Co, H, W, k);
+  const Conv2dModBwdWs L = conv2dmod_bwd_ws(B, Ci, Co, H, W, k, precision);
   if (ws_bytes < L.total) return fail(SX_ENOMEM, "workspace %zu bytes < required %zu", ws_bytes, L.total);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto H16 = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   float *gz = F(L.gz), *xm = F(L.xm), *wT = F(L.wT), *wsq = F(L.wsq), *dcoef = F(L.dcoef), *gdot = F(L.gdot), *gm1 = F(L.gm1),
         *msq = F(L.msq), *partial = F(L.partial);
   const int HW = H * W, taps = k * k;
+  const long long n_g = (long long)B * Co * HW, n_x = (long long)B * Ci * HW;
   // packed operands: wsq[i][o], flipped / transposed weights for the dgrad
   pack_weights_kernel<<<ew_grid((long long)Ci * Co, 256), 256, 0, st>>>(weight, nullptr, nullptr, wsq, Co, Ci, taps);
-  SX_CHECK_LAUNCH();
-  pack_weights_dgrad_kernel<<<ew_grid((long long)Ci * Co, 256), 256, 0, st>>>(weight, wT, Co, Ci, taps);
   SX_CHECK_LAUNCH();
   if (demod) {
     DemodParams dp{};
@@ -182,19 +202,31 @@ int sx_conv2dmod_bwd(const float* x, const float* weight, const float* style, co
     dp.first_conv = 0; dp.num_convs = 1; dp.styles = style; dp.style_stride = Ci; dp.dcoef = dcoef; dp.dcoef_stride = Co; dp.eps = eps;
     SX_TRY(launch_demod(dp, B, Ci, Co, st));
   }
-  // gz = g * d (NHWC)
-  nchw_to_nhwc_scale_kernel<<<dim3((HW + 31) / 32, (Co + 31) / 32, B), 256, 0, st>>>(grad_out, demod ? dcoef : nullptr, gz, Co, HW);
-  SX_CHECK_LAUNCH();
-  // dgrad: gxm = conv(W^T flipped, gz) -> grad_x (NCHW), then gm1 = <gxm, x> per plane and grad_x *= m in place
+  const float* dscale = demod ? dcoef : nullptr;
+  const dim3 grid_g((HW + 31) / 32, (Co + 31) / 32, B), grid_x((HW + 31) / 32, (Ci + 31) / 32, B);
+  // ---- dgrad: gxm = conv(W^T flipped, g * d) -> grad_x (NCHW fp32)
   {
-    ConvSimtParams p;
-    p.x = gz; p.x_bstride = (long long)HW * Co; p.wpk = wT;
-    p.B = B; p.Ci = Co; p.Co = Ci; p.H = H; p.W = W; p.KS = k;
     ConvEpilogue ep{};
     ep.out = grad_x; ep.out_nchw_f32 = 1;
-    p.ep = ep;
-    SX_TRY(launch_conv_simt(p, st));
+    if (L.dgrad_tc) {
+      pack_weights_dgrad_bf16_kernel<<<ew_grid((long long)Ci * Co, 256), 256, 0, st>>>(weight, H16(L.wT_bf), Co, Ci, taps);
+      SX_CHECK_LAUNCH();
+      nchw_to_nhwc_scale_kernel<__nv_bfloat16><<<grid_g, 256, 0, st>>>(grad_out, dscale, H16(L.gz_bf), Co, HW);
+      SX_CHECK_LAUNCH();
+      SX_TRY(tc::launch_conv_bf16(H16(L.gz_bf), H16(L.wT_bf), B, Co, Ci, H, W, k, ep, st));
+    } else {
+      pack_weights_dgrad_kernel<<<ew_grid((long long)Ci * Co, 256), 256, 0, st>>>(weight, wT, Co, Ci, taps);
+      SX_CHECK_LAUNCH();
+      nchw_to_nhwc_scale_kernel<float><<<grid_g, 256, 0, st>>>(grad_out, dscale, gz, Co, HW);
+      SX_CHECK_LAUNCH();
+      ConvSimtParams p;
+      p.x = gz; p.x_bstride = (long long)HW * Co; p.wpk = wT;
+      p.B = B; p.Ci = Co; p.Co = Ci; p.H = H; p.W = W; p.KS = k;
+      p.ep = ep;
+      SX_TRY(launch_conv_simt(p, st));
+    }
   }
+  // gm1 = <gxm, x> per plane, then grad_x = gxm * (style + 1) in place
   plane_dot_kernel<<<(unsigned)((long long)B * Ci), 256, 0, st>>>(grad_x, x, style, gm1, HW);
   SX_CHECK_LAUNCH();
   if (demod) {
@@ -206,20 +238,32 @@ int sx_conv2dmod_bwd(const float* x, const float* weight, const float* style, co
   }
   style_grad_kernel<<<(unsigned)(((long long)B * Ci * 32 + 255) / 256), 256, 0, st>>>(gm1, style, demod ? gdot : nullptr, wsq, grad_style, B, Ci, Co);
   SX_CHECK_LAUNCH();
-  // wgrad over the modulated activations
-  nchw_to_nhwc_modulate_kernel<float><<<dim3((HW + 31) / 32, (Ci + 31) / 32, B), 256, 0, st>>>(x, style, xm, Ci, HW);
-  SX_CHECK_LAUNCH();
-  {
+  // ---- wgrad over the modulated activations
+  int splits = L.splits;
+  if (L.wgrad_tc) {
+    splits = L.splits_tc;
+    nchw_scale_bf16_kernel<<<ew_grid(n_g, 256), 256, 0, st>>>(grad_out, dscale, 0.f, H16(L.gzp_bf), HW, n_g);
+    SX_CHECK_LAUNCH();
+    nchw_scale_shift_bf16_kernel<<<ew_grid(n_x, 256), 256, 0, st>>>(x, style, H16(L.xmp_bf), HW, W, k, n_x);
+    SX_CHECK_LAUNCH();
+    SX_TRY(tc::launch_wgrad_tc(H16(L.gzp_bf), H16(L.xmp_bf), partial, B, Ci, Co, H, W, k, splits, st));
+  } else {
+    if (L.dgrad_tc) {   // the FFMA wgrad reads fp32 NHWC g * d, which the tensor-core dgrad did not produce
+      nchw_to_nhwc_scale_kernel<float><<<grid_g, 256, 0, st>>>(grad_out, dscale, gz, Co, HW);
+      SX_CHECK_LAUNCH();
+    }
+    nchw_to_nhwc_modulate_kernel<float><<<grid_x, 256, 0, st>>>(x, style, xm, Ci, HW);
+    SX_CHECK_LAUNCH();
     WgradParams p;
     p.gz = gz; p.xm = xm; p.partial = partial;
-    p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KS = k; p.splits = L.splits;
+    p.B = B; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KS = k; p.splits = splits;
     const long long M = (long long)B * HW;
-    p.pix_per_split = ((M + L.splits - 1) / L.splits + 15) / 16 * 16;
-    dim3 grid((unsigned)(((Co + 63) / 64) * ((Ci + 63) / 64)), (unsigned)taps, (unsigned)L.splits);
+    p.pix_per_split = ((M + splits - 1) / splits + 15) / 16 * 16;
+    dim3 grid((unsigned)(((Co + 63) / 64) * ((Ci + 63) / 64)), (unsigned)taps, (unsigned)splits);
     wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
     SX_CHECK_LAUNCH();
   }
-  wgrad_reduce_kernel<<<ew_grid((long long)Co * Ci, 256), 256, 0, st>>>(partial, L.splits, weight, demod ? gdot : nullptr, msq, grad_weight,
+  wgrad_reduce_kernel<<<ew_grid((long long)Co * Ci, 256), 256, 0, st>>>(partial, splits, weight, demod ? gdot : nullptr, msq, grad_weight,
                                                                       B, Co, Ci, taps);
   SX_CHECK_LAUNCH();
   return SX_OK;

@@ -33,8 +33,9 @@ __global__ void pack_weights_dgrad_kernel(const float* __restrict__ W, float* __
 }
 
 // NCHW fp32 -> NHWC fp32 with an optional per-(b, c) scale (no "+1": the demodulation coefficients are used as they are)
+template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_scale_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                                 float* __restrict__ out, int C, int HW) {
+                                                                 T* __restrict__ out, int C, int HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -51,7 +52,40 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_scale_kernel(const float* __
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int p = p0 + j, c = c0 + tx;
-    if (c < C && p < HW) out[((long long)b * HW + p) * C + c] = tile[tx][j];
+    if (c < C && p < HW) out[((long long)b * HW + p) * C + c] = from_f<T>(tile[tx][j]);
+  }
+}
+
+// bf16 operands of the tensor-core backward ------------------------------------------------------------------------
+// dgrad weights, K-major for the tcgen05 conv kernels: wT[i][tap' * Co + o] = W[o][i][tap], tap' = flipped tap
+__global__ void pack_weights_dgrad_bf16_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ wT, int Co, int Ci, int taps) {
+  const long long total = (long long)Co * Ci;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(e / Ci), c = (int)(e - (long long)o * Ci);
+    for (int t = 0; t < taps; ++t) wT[(long long)c * taps * Co + (long long)(taps - 1 - t) * Co + o] = __float2bfloat16_rn(W[e * taps + t]);
+  }
+}
+// NCHW fp32 -> NCHW bf16 with a per-(b, c) plane scale: scale[plane] (+ add), e.g. d[b,o] or style[b,i] + 1
+__global__ void __launch_bounds__(256) nchw_scale_bf16_kernel(const float* __restrict__ x, const float* __restrict__ scale, float add,
+                                                              __nv_bfloat16* __restrict__ out, int HW, long long total) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const float sc = scale ? __ldg(scale + e / HW) + add : 1.f;
+    out[e] = __float2bfloat16_rn(x[e] * sc);
+  }
+}
+// the wgrad_tc B operand: `copies` (1 or 3) NCHW bf16 copies of x * (style + 1), copy s shifted by dx = s - copies/2 along x with
+// zero padding:  out[s][b,c,y,x] = xm[b,c,y,x+dx]   (TMA cannot start a box at an odd pixel of the innermost dimension)
+__global__ void __launch_bounds__(256) nchw_scale_shift_bf16_kernel(const float* __restrict__ x, const float* __restrict__ style,
+                                                                    __nv_bfloat16* __restrict__ out, int HW, int W, int copies,
+                                                                    long long total) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const float sc = __ldg(style + e / HW) + 1.f;
+    const int xx = (int)(e % W);
+    for (int s = 0; s < copies; ++s) {
+      const int dx = s - copies / 2;
+      const bool in = xx + dx >= 0 && xx + dx < W;
+      out[(long long)s * total + e] = __float2bfloat16_rn(in ? x[e + dx] * sc : 0.f);
+    }
   }
 }
 

@@ -17,7 +17,9 @@ Two levels:
 Autograd (first slice): at module level every op is a ``torch.autograd.Function`` whose
 forward AND first-order backward are native kernels (``csrc/conv_bwd.cuh``, ``csrc/bwd_ops.cuh``), fp32, deterministic.
 ``Generator.forward`` takes that path when gradients are being recorded; under ``torch.no_grad()`` (AttFind, rendering)
-it runs the fused plan, which records nothing.  Not twice differentiable (no path-length / gradient penalty yet).
+it runs the fused plan, which records nothing.  With ``precision = "bf16"`` the 3x3 modulated convolutions run forward,
+dgrad and wgrad on the tcgen05 kernels (bf16 operands, fp32 accumulation).  Not twice differentiable (no path-length /
+gradient penalty yet).
 """
 from __future__ import annotations
 
@@ -273,12 +275,20 @@ class Conv2DMod(nn.Module):
         co, ci, k, _ = self.weight.shape
         if c != ci or y.shape != (b, ci):
             raise ValueError(f"Conv2DMod: x {tuple(x.shape)} / style {tuple(y.shape)} do not match weight {tuple(self.weight.shape)}")
-        if (_prec(self) == N.PREC_FP32 and torch.is_grad_enabled()
-                and (x.requires_grad or y.requires_grad or self.weight.requires_grad)):
-            # training: the native forward + the native first-order backward (sx_conv2dmod_bwd).  The backward kernels are
-            # fp32; the bf16 module records no graph (inference precision, as before).
-            return Conv2DModFunction.apply(x, y, self.weight, bool(self.demod), float(self.eps))
+        if _wants_grad(x, y, self.weight):
+            # training: the native forward + the native first-order backward (sx_conv2dmod_bwd).  precision "bf16" runs the
+            # forward, the dgrad and the wgrad on the tensor cores where the kernels take the shape (3x3, tensor-core channel
+            # counts, power-of-two maps) and this conv in fp32 otherwise (the 1x1 ToRGB convs)
+            prec = _prec(self)
+            if prec == N.PREC_BF16 and not _tc_shape_ok(ci, co, x.shape[2], x.shape[3], k):
+                prec = N.PREC_FP32
+            return Conv2DModFunction.apply(x, y, self.weight, bool(self.demod), float(self.eps), prec)
         return _conv2dmod_forward(x, y, self.weight.detach(), bool(self.demod), float(self.eps), _prec(self))
+
+
+def _tc_shape_ok(ci, co, h, w, k) -> bool:
+    """mirror of tc::tc_shape_supported (csrc/conv_tc.cuh): shapes the bf16 tcgen05 conv kernels take."""
+    return (k == 3 and ci % 32 == 0 and (co in (32, 64, 128) or co % 256 == 0) and h == w and w >= 4 and (w & (w - 1)) == 0)
 
 
 def _conv2dmod_forward(x, y, w, demod, eps, prec):
@@ -295,17 +305,18 @@ def _conv2dmod_forward(x, y, w, demod, eps, prec):
 
 
 class Conv2DModFunction(torch.autograd.Function):
-    """Conv2DMod.forward (ST:647-667) with its first-order backward on the native kernels (``csrc/conv_bwd.cuh``):
+    """Conv2DMod.forward (ST:647-667) with its first-order backward on the native kernels (``csrc/conv_bwd.cuh``; with
+    ``prec`` = bf16 the forward, the dgrad and the wgrad run on the tcgen05 kernels, ``csrc/wgrad_tc.cuh``):
     grad_x (dgrad through the shared weights), grad_weight (wgrad over all pixels of the batch + the demodulation term)
     and grad_style (modulation + demodulation terms).  Not twice differentiable: the path-length and gradient penalties
     of the training step (ST:296-316) need a double backward that is not built."""
 
     @staticmethod
-    def forward(ctx, x, y, weight, demod, eps):
+    def forward(ctx, x, y, weight, demod, eps, prec=N.PREC_FP32):
         xd, yd, wdt = N.f32c(x.detach()), N.f32c(y.detach()), N.f32c(weight.detach())
-        out = _conv2dmod_forward(xd, yd, wdt, demod, eps, N.PREC_FP32)
+        out = _conv2dmod_forward(xd, yd, wdt, demod, eps, prec)
         ctx.save_for_backward(xd, yd, wdt, out)
-        ctx.demod, ctx.eps = demod, eps
+        ctx.demod, ctx.eps, ctx.prec = demod, eps, prec
         return out
 
     @staticmethod
@@ -320,11 +331,11 @@ class Conv2DModFunction(torch.autograd.Function):
         gx = torch.empty_like(x)
         gy = torch.empty_like(y)
         gw = torch.empty_like(w)
-        ws = _op_ws.get(lib.sx_conv2dmod_bwd_workspace_bytes(b, ci, co, h, wd, k), x.device)
+        ws = _op_ws.get(lib.sx_conv2dmod_bwd_workspace_bytes(b, ci, co, h, wd, k, ctx.prec), x.device)
         N.check(lib.sx_conv2dmod_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), out.data_ptr(), g.data_ptr(), gx.data_ptr(),
                                      gw.data_ptr(), gy.data_ptr(), b, ci, co, h, wd, k, 1 if ctx.demod else 0, ctx.eps,
-                                     ws.data_ptr(), ws.numel(), N.stream_ptr()), "sx_conv2dmod_bwd")
-        return gx, gy, gw, None, None
+                                     ctx.prec, ws.data_ptr(), ws.numel(), N.stream_ptr()), "sx_conv2dmod_bwd")
+        return gx, gy, gw, None, None, None
 
 
 class RGBBlock(nn.Module):
@@ -547,7 +558,7 @@ class Generator(nn.Module):
 
     def forward(self, styles, input_noise, get_style_coords=False):
         """styles [B, L, latent], input_noise [B|1, S, S, 1] -> rgb [B,3,S,S] (, style_coords [B, S_total])."""
-        if _prec(self) == N.PREC_FP32 and _wants_grad(styles, *self.parameters()):
+        if _wants_grad(styles, *self.parameters()):
             return self._forward_autograd(styles, input_noise, get_style_coords)
         plan = self.plan()
         styles_all = plan.styles(styles)
@@ -562,6 +573,8 @@ class Generator(nn.Module):
         convolution (ST:802,806) and goes through PyTorch like the encoder's convolutions."""
         N.require_cuda(styles, input_noise)
         batch_size = styles.shape[0]
+        for block in self.blocks:      # the 3x3 convs follow the generator's precision (tensor cores in "bf16")
+            block.conv1.precision = block.conv2.precision = self.precision
         x = self.initial_conv(self.initial_block).expand(batch_size, -1, -1, -1)
         rgb = None
         coords = []

@@ -67,15 +67,18 @@ int sx_conv2dmod_fwd(const float* x, const float* weight, const float* style, fl
                      int B, int Ci, int Co, int H, int W, int k, int demod, float eps, int precision,
                      void* workspace, size_t workspace_bytes, sx_stream_t stream);
 
-/* First-order backward of Conv2DMod.forward (what autograd derives for ST:647-667; training step),
- * fp32.  Inputs: the forward's x, weight, style, its output `out` (read only when demod != 0) and grad_out = dL/dout
+/* First-order backward of Conv2DMod.forward (what autograd derives for ST:647-667; training step).
+ * Inputs: the forward's x, weight, style, its output `out` (read only when demod != 0) and grad_out = dL/dout
  * [B,Co,H,W].  Outputs (all written): grad_x [B,Ci,H,W], grad_weight [Co,Ci,k,k] (summed over the batch: the weight is
  * shared), grad_style [B,Ci] (through the modulation and, with demod, through the demodulation coefficients).
+ * precision SX_PREC_FP32: FFMA implicit GEMMs.  SX_PREC_BF16: dgrad on the tcgen05 conv kernels (transposed weights) and
+ * wgrad as a tcgen05 GEMM over K = pixels where the shapes allow (dgrad: k == 3, channel counts as in sx_conv2dmod_fwd;
+ * wgrad: square power-of-two maps >= 64), FFMA otherwise; bf16 operands, fp32 accumulation and fp32 per-sample reductions.
  * Deterministic (fixed-order split-K reduction, no atomics).  B == 0 writes a zero grad_weight. */
-size_t sx_conv2dmod_bwd_workspace_bytes(int B, int Ci, int Co, int H, int W, int k);
+size_t sx_conv2dmod_bwd_workspace_bytes(int B, int Ci, int Co, int H, int W, int k, int precision);
 int sx_conv2dmod_bwd(const float* x, const float* weight, const float* style, const float* out, const float* grad_out,
                      float* grad_x, float* grad_weight, float* grad_style,
-                     int B, int Ci, int Co, int H, int W, int k, int demod, float eps,
+                     int B, int Ci, int Co, int H, int W, int k, int demod, float eps, int precision,
                      void* workspace, size_t workspace_bytes, sx_stream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) -- ST:614,679.  [B,C,H,W] -> [B,C,2H,2W] */

@@ -25,6 +25,8 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                help="bf16: the 3x3 modulated convs run forward / dgrad / wgrad on the tcgen05 kernels where they take the shape")
 a = ap.parse_args()
 
 torch.backends.cudnn.allow_tf32 = False
@@ -34,6 +36,7 @@ sd = synthetic.make_generator_state(a.size, seed=42)
 G = sx.Generator(a.size, 514).to(dev)
 G.load_state_dict(sd, strict=False)
 G.train()
+G.precision = a.precision
 pairs = synthetic.generator_pairs(a.size)
 fwd_flops = 0.0
 for l, (ci, co) in enumerate(pairs):
@@ -65,8 +68,8 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 line = {"metric": "generator_fwd_bwd_images_per_sec", "value": a.batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
-        "config": {"workload": f"StylEx {a.size}px generator forward + backward of <rgb, g>, batch {a.batch}, fp32 native kernels"},
-        "dtype": "f32", "gpu_launches": (_native.launch_count() - l0) // a.steps,
+        "config": {"workload": f"StylEx {a.size}px generator forward + backward of <rgb, g>, batch {a.batch}, {a.precision} native kernels"},
+        "dtype": "f32" if a.precision == "fp32" else "bf16", "gpu_launches": (_native.launch_count() - l0) // a.steps,
         "tflops": 3.0 * fwd_flops * a.batch / (ms * 1e-3) / 1e12, "mem_gb": torch.cuda.max_memory_allocated() / 1e9}
 if not a.no_cpu:
     from oracle import stylex_oracle as O

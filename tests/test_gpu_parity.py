@@ -713,7 +713,7 @@ def test_conv2dmod_backward_matches_oracle_fp64(dev, b, ci, co, hw, k, demod):
 
 def test_conv2dmod_backward_properties(dev):
     """size-independent properties: linear in the upstream gradient; a zero upstream gradient gives exact zeros; the
-    bf16 (inference) module and torch.no_grad() record no graph; an empty batch gives a zero weight gradient."""
+    torch.no_grad() records no graph; an empty batch gives a zero weight gradient."""
     g = torch.Generator().manual_seed(9)
     b, ci, co, hw = 2, 32, 32, 16
     x = torch.randn(b, ci, hw, hw, generator=g).to(dev)
@@ -734,13 +734,9 @@ def test_conv2dmod_backward_properties(dev):
         assert float(gz.abs().max()) == 0.0
     with torch.no_grad():
         assert not conv(x, y).requires_grad
-    conv.precision = "bf16"
-    with torch.enable_grad():
-        assert not conv(x.clone().requires_grad_(True), y).requires_grad
-    conv.precision = "fp32"
     lib = _native.lib()
     gw = torch.ones(co, ci, 3, 3, device=dev)
-    _native.check(lib.sx_conv2dmod_bwd(0, 0, 0, 0, 0, 0, gw.data_ptr(), 0, 0, ci, co, hw, hw, 3, 1, 1e-8, 0, 0, _native.stream_ptr()),
+    _native.check(lib.sx_conv2dmod_bwd(0, 0, 0, 0, 0, 0, gw.data_ptr(), 0, 0, ci, co, hw, hw, 3, 1, 1e-8, 0, 0, 0, _native.stream_ptr()),
                   "sx_conv2dmod_bwd")
     assert float(gw.abs().max()) == 0.0
 
@@ -888,3 +884,63 @@ def test_resize_s2d_separable_equals_direct(dev, size, dtype):
     assert sep.shape == (5, 16, 115, 115)
     assert torch.equal(sep, direct)
     assert torch.equal(sep, space_to_depth_input(clf._native_pre(x)))
+
+
+@pytest.mark.parametrize("b,ci,co,hw,k,demod", [(2, 128, 128, 64, 3, True), (2, 32, 32, 64, 3, True), (4, 64, 32, 32, 3, True),
+                                                (3, 64, 3, 16, 1, False), (2, 32, 32, 128, 3, True)])
+def test_conv2dmod_backward_bf16_tensor_cores(dev, tc_ok, b, ci, co, hw, k, demod):
+    """precision bf16: dgrad on the tcgen05 conv kernels, wgrad as a tcgen05 GEMM over K = pixels (FFMA where a kernel does
+    not take the shape: k = 1 for the dgrad, maps narrower than 64 pixels for the wgrad), against float64 autograd through the oracle; tolerance 2e-2 of the largest
+    gradient entry (bf16 operands, fp32 accumulation); bit-reproducible."""
+    _need_tc(tc_ok)
+    g = torch.Generator().manual_seed(b * 100 + ci + hw)
+    x = torch.randn(b, ci, hw, hw, generator=g)
+    y = torch.randn(b, ci, generator=g) * 0.5
+    w = torch.randn(co, ci, k, k, generator=g) * (2.0 / (ci * k * k)) ** 0.5
+    go = torch.randn(b, co, hw, hw, generator=g)
+    _, gx_ref, gy_ref, gw_ref = O.modconv_grads(x, w, y, go, demod=demod)
+    lib = _native.lib()
+    xd, yd, wd, god = x.to(dev), y.to(dev), w.to(dev), go.to(dev)
+    ws = torch.empty(lib.sx_conv2dmod_workspace_bytes(b, ci, co, hw, hw, k, 0) + 256, dtype=torch.uint8, device=dev)
+    out = torch.empty(b, co, hw, hw, device=dev)
+    _native.check(lib.sx_conv2dmod_fwd(xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), out.data_ptr(), b, ci, co, hw, hw, k, int(demod), 1e-8,
+                                       0, ws.data_ptr(), ws.numel(), _native.stream_ptr()), "fwd")
+    res = []
+    for _ in range(2):
+        gx, gy, gw = torch.empty_like(xd), torch.empty_like(yd), torch.empty_like(wd)
+        wb = torch.empty(lib.sx_conv2dmod_bwd_workspace_bytes(b, ci, co, hw, hw, k, 1), dtype=torch.uint8, device=dev)
+        _native.check(lib.sx_conv2dmod_bwd(xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), out.data_ptr(), god.data_ptr(), gx.data_ptr(),
+                                           gw.data_ptr(), gy.data_ptr(), b, ci, co, hw, hw, k, int(demod), 1e-8, 1, wb.data_ptr(),
+                                           wb.numel(), _native.stream_ptr()), "sx_conv2dmod_bwd bf16")
+        torch.cuda.synchronize()
+        res.append((gx, gy, gw))
+    assert _rel(res[0][0], gx_ref) <= BF16_TOL
+    assert _rel(res[0][1], gy_ref) <= BF16_TOL
+    assert _rel(res[0][2], gw_ref) <= BF16_TOL
+    for a, c in zip(res[0], res[1]):
+        assert torch.equal(a, c)
+
+
+def test_generator_backward_bf16(dev, tc_ok):
+    """Generator.forward with precision "bf16" and gradients recorded: the 3x3 modulated convs run forward / dgrad / wgrad on
+    the tensor cores; parameter and style gradients within the bf16 tolerance of float64 autograd through the oracle."""
+    _need_tc(tc_ok)
+    size = 64
+    sd = synthetic.make_generator_state(size, seed=42)
+    G = g_module(sd, size, 16, dev).train()
+    G.precision = "bf16"
+    lat = synthetic.make_latents(2, 5)
+    styles = O.styles_def_to_tensor([(lat, G.num_layers)])
+    noise = synthetic.make_noise(size, 42)
+    go = torch.randn(2, 3, size, size, generator=torch.Generator().manual_seed(1))
+    rgb_ref, ref, ref_st = O.generator_grads(sd, styles, noise, go, dtype=torch.float64)
+    with torch.enable_grad():
+        st = styles.to(dev).requires_grad_(True)
+        rgb = G(st, noise.to(dev))
+        (rgb * go.to(dev)).sum().backward()
+    assert _rel(rgb.detach(), rgb_ref) <= BF16_TOL
+    params = dict(G.named_parameters())
+    for n in ("initial_conv.weight", "blocks.0.conv1.weight", "blocks.1.conv2.weight", "blocks.2.conv1.weight", "blocks.3.conv2.weight",
+              "blocks.4.conv1.weight", "blocks.4.to_style2.weight", "blocks.3.to_rgb.conv.weight", "blocks.2.to_noise1.weight"):
+        assert _rel(params[n].grad, ref[n]) <= 3e-2, n
+    assert _rel(st.grad, ref_st) <= 3e-2
