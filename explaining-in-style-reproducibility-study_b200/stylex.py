@@ -330,6 +330,8 @@ def encode_images(stylex, classifier, images: torch.Tensor, noise: Optional[torc
             if use_old_architecture:
                 d = stylex.D(gen)
             else:
+                # the new architecture's discriminator (stylex_train_new.py) is conditioned on the class probabilities; a
+                # discriminator with that forward signature works here, this package's DiscriminatorE is the old one
                 d = stylex.D(gen, probabilities=torch.softmax(classifier.classify_images(gen), dim=1))
             out["discriminator"][i: i + batch] = d.reshape(-1, 1)
     return out
