@@ -52,3 +52,50 @@ def test_product_classifier_wrappers_match_reference_wrappers():
         ref = RL.reference_classifier(kind, net, 64).classify_images(x)
         mine = sx.make_classifier(kind, net, 64).classify_images(x)
         assert torch.equal(ref, mine), kind
+
+
+def test_oracle_discriminator_matches_reference_module():
+    """DiscriminatorE as encoder and as discriminator at 32px / capacity 8, fresh seeds (beyond frontend_small.npz)."""
+    R = RL.load_reference()
+    g = torch.Generator().manual_seed(5)
+    images = torch.rand(3, 3, 32, 32, generator=g)
+    for enc in (True, False):
+        m = R.DiscriminatorE(32, 8, encoder=enc).eval()
+        sd = synthetic.make_discriminator_state(32, seed=77, network_capacity=8, encoder=enc)
+        r = m.load_state_dict(sd, strict=False)
+        assert not r.unexpected_keys and all(k.endswith(".f") for k in r.missing_keys)
+        assert (m(images) - O.discriminator_forward(sd, images)).abs().max().item() <= 2e-6
+        assert m(images[:1]).shape == O.discriminator_forward(sd, images[:1]).shape
+
+
+def test_product_stylex_loads_a_reference_state_dict_strictly():
+    """a state dict produced by the reference StylEx class loads into the drop-in container with strict=True, and the
+    reverse (what Trainer.load does with a checkpoint written by save_checkpoint)."""
+    R = RL.load_reference()
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        with RL.cpu_cuda_identity():
+            ref = R.StylEx(image_size=32, network_capacity=4)
+        mine = sx.StylEx(image_size=32, network_capacity=4)
+    finally:
+        torch.cuda.is_available = real
+    mine.load_state_dict(ref.state_dict())                   # strict
+    ref.load_state_dict(mine.state_dict())
+    for (k, a), (k2, b) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert k == k2 and torch.equal(a, b), k
+
+
+@pytest.mark.parametrize("ci,co,k,demod,hw", [(6, 10, 3, True, 5), (12, 3, 1, False, 7), (32, 32, 3, True, 8)])
+def test_oracle_conv_gradients_match_reference_autograd(ci, co, k, demod, hw):
+    R = RL.load_reference()
+    g = torch.Generator().manual_seed(ci * 10 + hw)
+    m = R.Conv2DMod(ci, co, k, demod=demod)
+    x, y = torch.randn(2, ci, hw, hw, generator=g), torch.randn(2, ci, generator=g) * 0.6
+    go = torch.randn(2, co, hw, hw, generator=g)
+    with torch.enable_grad():
+        xs, ys = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        ref = torch.autograd.grad(m(xs, ys), (xs, ys, m.weight), go)
+    _, gx, gy, gw = O.modconv_grads(x, m.weight.detach(), y, go, demod=demod)
+    for got, r in zip((gx, gy, gw), ref):
+        assert (got.float() - r).abs().max().item() <= 2e-5 * max(1.0, r.abs().max().item())
