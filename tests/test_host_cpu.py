@@ -225,3 +225,28 @@ def test_checkpoint_round_trip(tmp_path):
     m4, cfg4 = sx.load_checkpoint(tmp_path / "models", "run", 12)
     assert cfg4["image_size"] == 16 and cfg4["network_capacity"] == 4
     assert torch.equal(m4.encoder.fc.weight.cpu(), m.encoder.fc.weight.cpu())
+
+
+def test_built_library_contains_tcgen05_and_tma_sass():
+    """the hot kernels really are tcgen05 / TMEM / TMA code: every conv_tc / conv_tc_halo / wgrad_tc instantiation in the built
+    library issues UTCHMMA (tcgen05.mma), UTMALDG (cp.async.bulk.tensor) and LDTM (tcgen05.ld) -- checked on the SASS, no GPU."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run([cuobjdump, "-sass", _native.LIB_PATH], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    kernels, cur = {}, None
+    for line in r.stdout.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            kernels[cur] = set()
+        elif cur is not None:
+            for op in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "HMMA.", "IMMA."):
+                if op in line:
+                    kernels[cur].add(op)
+    hot = {k: v for k, v in kernels.items() if any(t in k for t in ("conv_tc_kernel", "conv_tc_halo_kernel", "wgrad_tc_kernel"))}
+    assert len(hot) >= 20, sorted(hot)
+    for k, ops in hot.items():
+        assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= ops, (k, ops)
+        assert not ({"HMMA.", "IMMA."} & ops), (k, ops)      # no legacy mma.sync path inside the tensor-core kernels
