@@ -250,3 +250,40 @@ def test_built_library_contains_tcgen05_and_tma_sass():
     for k, ops in hot.items():
         assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"} <= ops, (k, ops)
         assert not ({"HMMA.", "IMMA."} & ops), (k, ops)      # no legacy mma.sync path inside the tensor-core kernels
+
+
+def test_coord_runs_and_shards_properties():
+    """hypothesis: for any subset of style coordinates and any batch size, the runs are contiguous, stay inside one conv's
+    coordinate range, respect the half-batch cap and cover the subset exactly once; shards tile [0, n) in rank order."""
+    from hypothesis import given, settings, strategies as st
+
+    pairs = synthetic.generator_pairs(32, network_capacity=4)
+    conv_coords, off = [], 0
+    for ci, co in pairs:
+        conv_coords += [(off, ci), (off + ci, co)]
+        off += ci + co
+    S = off
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.sets(st.integers(0, S - 1), max_size=80), st.integers(1, 40))
+    def runs_ok(sind, half):
+        runs = attfind._coord_runs(conv_coords, sorted(sind) if sind else None, half)
+        seen = []
+        for conv, first, cnt in runs:
+            lo, width = conv_coords[conv]
+            assert 1 <= cnt <= half and lo <= first and first + cnt <= lo + width
+            seen += list(range(first, first + cnt))
+        assert sorted(seen) == (sorted(sind) if sind else list(range(S))) and len(seen) == len(set(seen))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 300), st.integers(1, 16))
+    def shards_ok(n, world):
+        edges = [attfind.shard_range(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (a, b), (c, d) in zip(edges, edges[1:]):
+            assert b == c and a <= b
+        sizes = [b - a for a, b in edges]
+        assert max(sizes) - min(sizes) <= 1
+
+    runs_ok()
+    shards_ok()
