@@ -12,10 +12,11 @@ from . import _native  # noqa: F401
 from .modules import (Blur, Conv2DMod, Conv2DModFunction, Generator, GeneratorBlock, GeneratorPlan, RGBBlock, image_noise,  # noqa: F401
                       styles_def_to_tensor)
 from .classifiers import MobileNet, ResNet, make_classifier  # noqa: F401
-from .attfind import (attfind_extraction, attfind_select, attfind_sweep, find_significant_styles,  # noqa: F401
-                      get_min_max_style_vectors, sindex_to_block_idx_and_index)
+from .attfind import (attfind_extraction, attfind_select, attfind_sweep, filter_unstable_images,  # noqa: F401
+                      find_significant_styles, get_min_max_style_vectors, load_records, save_records,
+                      sindex_to_block_idx_and_index)
 from .counterfactual import (draw_on_image, generate_change_image_given_dlatent, generate_images_given_dlatent,  # noqa: F401
-                             render_counterfactuals, visualize_style)
+                             render_counterfactuals, visualize_style, visualize_style_by_distance_in_s)
 from .stylex import (DiscriminatorBlock, DiscriminatorE, EqualLinear, StyleVectorizer, StylEx, encode_images,  # noqa: F401
                      load_checkpoint, load_stylex, model_loader, save_checkpoint, stylex_config)
 

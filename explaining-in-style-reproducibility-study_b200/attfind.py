@@ -345,3 +345,36 @@ def save_records(results_folder: str, datasets: Dict[str, torch.Tensor]) -> str:
         for k, v in arrays.items():
             f.create_dataset(k, v.shape, dtype="f")[:] = v
     return path
+
+
+def load_records(path: str, threshold_index: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """NB cell 12: read ``style_change_records`` back (``.npz`` written by ``save_records``, or the reference's ``.hdf5`` when
+    h5py is importable) and derive what the selection / visualisation cells use.  ``threshold_index`` = the notebook's
+    ``load_hdf5_results(..., threshold)`` row cap (501 there).  Returns the nine datasets (``noise`` / ``minima`` / ``maxima``
+    unsliced, like cell 12) plus ``style_min`` / ``style_max`` [S] and ``all_style_vectors_distances`` [N, S, 2]."""
+    if path.endswith((".hdf5", ".h5")):
+        import h5py
+        with h5py.File(path, "r") as f:
+            raw = {k: np.array(f[k]) for k in DATASET_NAMES}
+    else:
+        with np.load(path) as z:
+            raw = {k: np.array(z[k]) for k in DATASET_NAMES}
+    out = {k: (v if k in ("noise", "minima", "maxima") else v[:threshold_index]) for k, v in raw.items()}
+    out["style_min"] = np.squeeze(out["minima"])
+    out["style_max"] = np.squeeze(out["maxima"])
+    sc = out["style_coordinates"]
+    dist = np.zeros((sc.shape[0], sc.shape[1], 2))                                       # float64, like cell 12
+    dist[:, :, 0] = sc - np.tile(out["style_min"], (sc.shape[0], 1))
+    dist[:, :, 1] = np.tile(out["style_max"], (sc.shape[0], 1)) - sc
+    out["all_style_vectors_distances"] = dist
+    return out
+
+
+def filter_unstable_images(style_change_effect, effect_threshold=0.3, num_indices_threshold=150):
+    """NB cell 11 (defined there, its call is commented out at NB:664): zero the rows of images for which more than
+    ``num_indices_threshold`` (direction, coordinate, class) entries move the logits by more than ``effect_threshold``.
+    In place, like the notebook; returns the array."""
+    unstable_images = (np.sum(np.abs(style_change_effect) > effect_threshold, axis=(1, 2, 3)) > num_indices_threshold)
+    style_change_effect[unstable_images] = 0
+    return style_change_effect
+

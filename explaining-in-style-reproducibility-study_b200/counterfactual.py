@@ -126,3 +126,32 @@ def visualize_style(generator, classifier, all_dlatents, style_change_effect, st
     if len(result_images) < 3:
         return np.array([])           # "No point in returning results with very little images" (NB cell 20)
     return np.concatenate(result_images[:max_images], axis=0)
+
+
+def visualize_style_by_distance_in_s(generator, classifier, all_dlatents, all_style_vectors_distances, style_min, style_max, sindex,
+                                     style_sign_index, max_images, shift_size, font_file=None, noise=None, label_size=2,
+                                     class_index=0, draw_results_on_image=True, effect_threshold=0.1, cuda_rank=0):
+    """NB cell 21: the images whose style coordinate ``sindex`` lies FARTHEST from the extreme it is pushed to
+    (``all_style_vectors_distances[:, sindex, style_sign_index]`` descending, cell 12), rendered base | counterfactual and
+    stacked; at most ``max_images`` panels out of the first ``10 * max_images`` candidates, nothing below 3 panels.  (Like the
+    notebook, ``effect_threshold`` is accepted and unused.)"""
+    images_idx = np.argsort(np.asarray(all_style_vectors_distances)[:, sindex, style_sign_index])[::-1]
+    if images_idx.size == 0:
+        return np.array([])
+    images_idx = images_idx[: min(max_images * 10, len(images_idx))]
+    dlatents = np.asarray(all_dlatents)[images_idx]
+    result_images = []
+    for i in range(min(len(images_idx), max_images)):      # the notebook renders all candidates and keeps the first max_images
+        panel, _, _ = generate_images_given_dlatent(dlatent=dlatents[i: i + 1], generator=generator, classifier=classifier,
+                                                    class_index=class_index, sindex=sindex, noise=noise,
+                                                    s_style_min=style_min[sindex], s_style_max=style_max[sindex],
+                                                    style_direction_index=style_sign_index, font_file=font_file,
+                                                    shift_size=shift_size, label_size=label_size,
+                                                    draw_results_on_image=draw_results_on_image,
+                                                    resolution=generator.image_size, cuda_rank=cuda_rank,
+                                                    gen_num_layers=generator.num_layers)
+        result_images.append(panel)
+    if len(images_idx) < 3:
+        return np.array([])
+    return np.concatenate(result_images[:max_images], axis=0)
+

@@ -287,3 +287,65 @@ def test_coord_runs_and_shards_properties():
 
     runs_ok()
     shards_ok()
+
+
+def test_records_round_trip_and_derived_arrays(tmp_path):
+    """save_records -> load_records (NB:394-417 / cell 12): the nine datasets come back, the row cap applies to the per-image
+    datasets only, and the derived distances are cell 12's float64 expressions."""
+    g = torch.Generator().manual_seed(0)
+    n, S = 7, 24
+    data = {"style_change": torch.randn(n, 2, S, 2, generator=g), "latents": torch.randn(n, 514, generator=g),
+            "base_prob": torch.randn(n, 2, generator=g), "minima": torch.randn(1, S, generator=g) - 3,
+            "maxima": torch.randn(1, S, generator=g) + 3, "style_coordinates": torch.randn(n, S, generator=g),
+            "original_images": torch.rand(n, 3, 8, 8, generator=g), "noise": torch.rand(1, 8, 8, 1, generator=g),
+            "discriminator": torch.randn(n, 1, generator=g)}
+    path = attfind.save_records(str(tmp_path), data)
+    rec = sx.load_records(path, threshold_index=5)
+    for k in attfind.DATASET_NAMES:
+        ref = data[k].numpy()
+        ref = ref if k in ("noise", "minima", "maxima") else ref[:5]
+        assert rec[k].dtype == np.float32 and np.array_equal(rec[k], ref), k
+    assert rec["style_min"].shape == (S,) and rec["all_style_vectors_distances"].dtype == np.float64
+    sc = data["style_coordinates"].numpy()[:5]
+    assert np.array_equal(rec["all_style_vectors_distances"][:, :, 0], sc - np.tile(rec["style_min"], (5, 1)))
+    assert np.array_equal(rec["all_style_vectors_distances"][:, :, 1], np.tile(rec["style_max"], (5, 1)) - sc)
+    assert sx.load_records(path)["latents"].shape == (n, 514)
+
+
+def test_filter_unstable_images():
+    rng = np.random.RandomState(1)
+    eff = rng.randn(6, 2, 40, 2) * 0.1
+    eff[2] = rng.randn(2, 40, 2) * 2.0            # image 2: almost every entry above the threshold
+    eff[4, 0, :10, 0] = 5.0                       # image 4: only 10 entries above it
+    before = eff.copy()
+    out = sx.filter_unstable_images(eff, effect_threshold=0.3, num_indices_threshold=100)
+    assert out is eff                             # in place, like the notebook
+    assert np.all(eff[2] == 0)
+    keep = [0, 1, 3, 4, 5]
+    assert np.array_equal(eff[keep], before[keep])
+
+
+def test_visualize_style_by_distance_host_logic(monkeypatch):
+    """NB cell 21's ordering / capping / stacking, with the (GPU-tested) renderer replaced by a stub that tags each panel."""
+    from stylex_b200 import counterfactual as cf
+
+    class G:
+        image_size, num_layers = 4, 3
+
+    calls = []
+
+    def fake(dlatent, **kw):
+        calls.append((float(dlatent[0, 0]), kw["sindex"], kw["style_direction_index"], kw["s_style_min"], kw["s_style_max"]))
+        return np.full((4, 8, 3), int(dlatent[0, 0]), np.uint8), 0.0, 0.0
+
+    monkeypatch.setattr(cf, "generate_images_given_dlatent", fake)
+    n, S = 9, 5
+    lat = np.arange(n, dtype=np.float32)[:, None] * np.ones((1, 514), np.float32)
+    dist = np.zeros((n, S, 2))
+    dist[:, 2, 1] = [0.3, 0.9, 0.1, 0.8, 0.5, 0.7, 0.2, 0.6, 0.4]
+    smin, smax = np.arange(S) - 10.0, np.arange(S) + 10.0
+    out = cf.visualize_style_by_distance_in_s(G, None, lat, dist, smin, smax, 2, 1, max_images=4, shift_size=1.5, noise=None)
+    assert out.shape == (16, 8, 3)
+    assert [int(out[4 * i, 0, 0]) for i in range(4)] == [1, 3, 5, 7]           # farthest first
+    assert all(c[1:] == (2, 1, -8.0, 12.0) for c in calls)
+    assert cf.visualize_style_by_distance_in_s(G, None, lat[:2], dist[:2], smin, smax, 2, 1, 4, 1.5).size == 0   # < 3 images

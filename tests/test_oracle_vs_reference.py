@@ -99,3 +99,13 @@ def test_oracle_conv_gradients_match_reference_autograd(ci, co, k, demod, hw):
     _, gx, gy, gw = O.modconv_grads(x, m.weight.detach(), y, go, demod=demod)
     for got, r in zip((gx, gy, gw), ref):
         assert (got.float() - r).abs().max().item() <= 2e-5 * max(1.0, r.abs().max().item())
+
+
+def test_filter_unstable_images_matches_notebook_cell():
+    ns = RL.notebook_namespace(True)
+    rng = np.random.RandomState(3)
+    eff = rng.randn(8, 2, 60, 2) * 0.25
+    eff[5] *= 6
+    a = ns["filter_unstable_images"](eff.copy(), 0.3, 100)
+    b = sx.filter_unstable_images(eff.copy(), 0.3, 100)
+    assert np.array_equal(a, b) and np.all(b[5] == 0) and np.any(b[0] != 0)
