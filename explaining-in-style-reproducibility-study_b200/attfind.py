@@ -263,8 +263,8 @@ def attfind_extraction(dataloader, num_images, results_folder, stylex, classifie
 
     Phase A (encode each image, classify it, build ``concat_w``, discriminator output and optional filter;
     NB:300-336) runs batched through ``stylex.encode_images`` (``front_batch`` images per launch; the dataloader
-    still yields one image per item, NB:284-285); phases B-C are ``attfind_sweep``.  Writes ``style_change_records.hdf5`` with the 9 datasets of NB:395-403 when h5py is
-    importable, else ``style_change_records.npz`` with the same names; also returns them as a dict.
+    still yields one image per item, NB:284-285); phases B-C are ``attfind_sweep``.  Writes ``style_change_records.hdf5`` with the 9 datasets of NB:395-403 (h5py when importable, else
+    the built-in minimal writer); also returns them as a dict.
     """
     if batch_size != 1:
         raise ValueError('Please use a batch_size equal to 1')                          # NB:284-285
@@ -331,16 +331,17 @@ def _pad(t: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def save_records(results_folder: str, datasets: Dict[str, torch.Tensor]) -> str:
-    """NB:394-417: the 9 float32 datasets of ``style_change_records.hdf5`` (npz when h5py is absent)."""
+    """NB:394-417: the 9 float32 datasets of ``style_change_records.hdf5`` -- through h5py when it is importable, else through
+    the built-in minimal HDF5 writer (``hdf5_lite``: superblock v0, contiguous datasets in the root group)."""
     arrays = {k: datasets[k].detach().float().cpu().numpy() for k in DATASET_NAMES}
     os.makedirs(results_folder, exist_ok=True)
+    path = os.path.join(results_folder, "style_change_records.hdf5")
     try:
         import h5py
     except ImportError:
-        path = os.path.join(results_folder, "style_change_records.npz")
-        np.savez(path, **arrays)
+        from . import hdf5_lite
+        hdf5_lite.write_hdf5(path, arrays)
         return path
-    path = os.path.join(results_folder, "style_change_records.hdf5")
     with h5py.File(path, "w") as f:
         for k, v in arrays.items():
             f.create_dataset(k, v.shape, dtype="f")[:] = v
@@ -348,14 +349,20 @@ def save_records(results_folder: str, datasets: Dict[str, torch.Tensor]) -> str:
 
 
 def load_records(path: str, threshold_index: Optional[int] = None) -> Dict[str, np.ndarray]:
-    """NB cell 12: read ``style_change_records`` back (``.npz`` written by ``save_records``, or the reference's ``.hdf5`` when
-    h5py is importable) and derive what the selection / visualisation cells use.  ``threshold_index`` = the notebook's
+    """NB cell 12: read ``style_change_records`` back (the ``.hdf5`` of ``save_records`` / of the reference, or an ``.npz``;
+    through h5py or the built-in reader) and derive what the selection / visualisation cells use.  ``threshold_index`` = the notebook's
     ``load_hdf5_results(..., threshold)`` row cap (501 there).  Returns the nine datasets (``noise`` / ``minima`` / ``maxima``
     unsliced, like cell 12) plus ``style_min`` / ``style_max`` [S] and ``all_style_vectors_distances`` [N, S, 2]."""
     if path.endswith((".hdf5", ".h5")):
-        import h5py
-        with h5py.File(path, "r") as f:
-            raw = {k: np.array(f[k]) for k in DATASET_NAMES}
+        try:
+            import h5py
+        except ImportError:
+            from . import hdf5_lite
+            allv = hdf5_lite.read_hdf5(path)
+            raw = {k: allv[k] for k in DATASET_NAMES}
+        else:
+            with h5py.File(path, "r") as f:
+                raw = {k: np.array(f[k]) for k in DATASET_NAMES}
     else:
         with np.load(path) as z:
             raw = {k: np.array(z[k]) for k in DATASET_NAMES}
