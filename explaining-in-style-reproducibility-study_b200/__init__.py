@@ -18,6 +18,7 @@ from .attfind import (attfind_extraction, attfind_select, attfind_sweep, filter_
 from .counterfactual import (draw_on_image, generate_change_image_given_dlatent, generate_images_given_dlatent,  # noqa: F401
                              render_counterfactuals, visualize_style, visualize_style_by_distance_in_s)
 from .stylex import (DiscriminatorBlock, DiscriminatorE, EqualLinear, StyleVectorizer, StylEx, encode_images,  # noqa: F401
-                     load_checkpoint, load_stylex, model_loader, save_checkpoint, stylex_config)
+                     find_discriminator_threshold, load_checkpoint, load_stylex, model_loader, save_checkpoint,
+                     stylex_config)
 
 __version__ = "0.1.0"

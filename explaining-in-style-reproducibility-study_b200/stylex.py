@@ -335,3 +335,57 @@ def encode_images(stylex, classifier, images: torch.Tensor, noise: Optional[torc
                 d = stylex.D(gen, probabilities=torch.softmax(classifier.classify_images(gen), dim=1))
             out["discriminator"][i: i + batch] = d.reshape(-1, 1)
     return out
+
+
+@torch.no_grad()
+def find_discriminator_threshold(stylex, classifier, dataloader, num_images, threshold_folder, dataset_name=None, image_size=64,
+                                 batch_size=1, cuda_rank=0, noise=None, use_old_architecture: bool = True, front_batch: int = 256):
+    """NB cell 5 ``find_discriminator_threshold``: the discriminator's output on the reconstruction of the first ``num_images``
+    images of ``dataloader`` (encode -> classify -> generate -> discriminate), written to ``discriminator_threshold.hdf5``
+    (datasets ``discriminator_outputs`` [N,1] and ``generated_images`` [N,3,S,S]) and returned.  ``front_batch`` images per
+    launch instead of the notebook's one; the notebook reads ``noise`` from its global scope, here it is an argument."""
+    if noise is None:
+        raise ValueError("find_discriminator_threshold needs the generator noise (a notebook global in the reference)")
+    dev = noise.device
+    G = stylex.G
+    outputs = torch.zeros(num_images, 1, device=dev)
+    generated = torch.zeros(num_images, 3, image_size, image_size, device=dev)
+    it = iter(dataloader)
+    done = 0
+    while done < num_images:
+        chunk = []
+        for image in it:
+            chunk.append(image.to(dev).reshape(-1, 3, image_size, image_size))
+            if len(chunk) >= min(front_batch, num_images - done):
+                break
+        if not chunk:
+            raise StopIteration(f"the dataloader ran out after {done} of {num_images} images")      # next(dataloader) in the notebook
+        x = torch.cat(chunk)[: num_images - done]
+        logits = classifier.classify_images(x).float()
+        w = stylex.encoder(x).reshape(x.shape[0], -1)
+        lat = torch.cat((w, logits if use_old_architecture else torch.softmax(logits, dim=1)), dim=1)
+        gen = G(styles_def_to_tensor([(lat, G.num_layers)]), noise)
+        if use_old_architecture:
+            d = stylex.D(gen)
+        else:
+            d = stylex.D(gen, probabilities=torch.softmax(classifier.classify_images(gen), dim=1))
+        k = x.shape[0]
+        outputs[done: done + k] = d.reshape(-1, 1)
+        generated[done: done + k] = gen
+        done += k
+    result = {"discriminator_outputs": outputs, "generated_images": generated}
+    if threshold_folder is not None:
+        os.makedirs(threshold_folder, exist_ok=True)
+        path = os.path.join(threshold_folder, "discriminator_threshold.hdf5")
+        arrays = {k: v.float().cpu().numpy() for k, v in result.items()}
+        try:
+            import h5py
+        except ImportError:
+            from . import hdf5_lite
+            hdf5_lite.write_hdf5(path, arrays)
+        else:
+            with h5py.File(path, "w") as f:
+                for k, v in arrays.items():
+                    f.create_dataset(k, v.shape, dtype="f")[:] = v
+    return result
+

@@ -390,3 +390,47 @@ def test_hdf5_lite_reads_a_genuine_hdf5_file_and_round_trips(tmp_path):
         H.write_hdf5(path, {f"d{i}": np.zeros(1, np.float32) for i in range(17)})
     with pytest.raises(TypeError):
         H.write_hdf5(path, {"c": np.zeros(2, np.complex64)})
+
+
+def test_find_discriminator_threshold_host_logic(tmp_path):
+    """NB cell 5's discriminator-threshold pass with CPU stand-ins for the four networks: batching, the concat_w construction
+    (old / new architecture), the two datasets it writes and their file."""
+    from stylex_b200 import hdf5_lite
+
+    class Enc(torch.nn.Module):
+        def forward(self, x):
+            return x.mean((2, 3)).repeat(1, 171)[:, :512].squeeze()          # [B,512] ([512] for one image, like ST:909)
+
+    class Gen:
+        num_layers, latent_dim = 3, 514
+
+        def __call__(self, styles, noise):
+            assert styles.shape[1:] == (3, 514)
+            return styles[:, 0, :48].reshape(-1, 3, 4, 4) + noise.reshape(1, 1, 4, 4)
+
+    class St:
+        pass
+
+    class Clf:
+        def classify_images(self, x):
+            return torch.stack([x.sum((1, 2, 3)), -x.sum((1, 2, 3))], 1) * 0.01
+
+    st = St()
+    st.encoder, st.G = Enc(), Gen()
+    st.D = lambda img: img.mean((1, 2, 3)).squeeze()
+    g = torch.Generator().manual_seed(0)
+    images = [torch.rand(1, 3, 4, 4, generator=g) for _ in range(7)]
+    noise = torch.rand(1, 4, 4, 1, generator=g)
+    res = sx.find_discriminator_threshold(st, Clf(), images, 5, str(tmp_path), image_size=4, noise=noise, front_batch=2)
+    assert res["discriminator_outputs"].shape == (5, 1) and res["generated_images"].shape == (5, 3, 4, 4)
+    # image by image, like the notebook
+    for i in range(5):
+        x = images[i]
+        lat = torch.cat((st.encoder(x).unsqueeze(0), Clf().classify_images(x)), 1)
+        gen = st.G(sx.styles_def_to_tensor([(lat, 3)]), noise)
+        assert torch.allclose(res["generated_images"][i], gen[0]) and torch.allclose(res["discriminator_outputs"][i, 0], st.D(gen))
+    back = hdf5_lite.read_hdf5(str(tmp_path / "discriminator_threshold.hdf5"))
+    assert sorted(back) == ["discriminator_outputs", "generated_images"]
+    assert np.array_equal(back["generated_images"], res["generated_images"].numpy())
+    with pytest.raises(StopIteration):
+        sx.find_discriminator_threshold(st, Clf(), images[:3], 5, None, image_size=4, noise=noise)
