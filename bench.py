@@ -17,8 +17,14 @@ e2e    = the same through the public API from HOST buffers: pinned latents + noi
          sweep, effects -> D2H, all inside the timed region.
 roofline = the Conv2DMod tcgen05 kernel: executed algorithmic FLOPs / CUDA-event time of those launches inside the
          timed region, against the measured sustained bf16 peak (MEASURED_PEAKS.json).
-cpu_baseline = the oracle (a CPU port of the reference loop: batch 1, one full generator forward per coord-eval)
-         on this box's host cores, on a bounded sample of the same workload.
+cpu_baseline = the reference's own loop on this box's host cores, on a bounded sample of the same workload: the VERBATIM
+         notebook cell 5 (`attfind_extraction`, NB:269-417) over the reference's own Generator / classifier wrapper when
+         `oracle/make_ref.sh` staged the reference files under oracle/_ref (kind "reference"), else the oracle port
+         (kind "port").  `--impl reference` times exactly the same thing, step by step.
+job    = (default on, `--no-job` to skip) ONE WHOLE AttFind job timed by the wall clock through the public API: host
+         latents -> H2D -> sweep of `--job-latents` latents per rank (128 x 8 ranks = BASELINE config 3; 256 x 1 at 64px =
+         config 2) -> the NCCL all-gather of the effects -> class split + greedy top-k on device -> picks on the host.
+         Reported beside the step rate so the gather, the selection, the per-job setup and the tail are all inside.
 """
 from __future__ import annotations
 
@@ -35,8 +41,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "attfind_coord_evals_per_sec_256px"
 UNIT = "coord-evals/s"
+
+
+def metric_name(size):
+    return f"attfind_coord_evals_per_sec_{size}px"
 
 
 def parse():
@@ -60,9 +69,14 @@ def parse():
     ap.add_argument("--latents-per-step", type=int, default=1)
     ap.add_argument("--pool", type=int, default=16, help="latents per rank prepared up front (minima/maxima pool)")
     ap.add_argument("--max-batch", type=int, default=256)
-    ap.add_argument("--cpu-sample-coords", type=int, default=160, help="style coordinates in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample-coords", type=int, default=60, help="style coordinates in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample-images", type=int, default=2, help="images in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-job", action="store_true", help="skip the whole-job leg")
+    ap.add_argument("--job-latents", type=int, default=0,
+                    help="latents PER RANK of the whole-job leg (default: 128 at 256px = config 3 on 8 ranks; 256 at 64px = config 2)")
+    ap.add_argument("--out", default=None, help="also append the JSON line to this file")
     return ap.parse_args()
 
 
@@ -141,67 +155,187 @@ def conv_flops_per_image(pairs):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(args, sd, model_cpu, noise, latents, minmax, n_coords, repeats=1):
-    """The reference algorithm (oracle port: batch 1, full G forward + classifier per coord-eval) on the host cores."""
-    import torch
-    import stylex_b200 as sx
-    from oracle import stylex_oracle as O
-
-    clf = sx.make_classifier(args.classifier, model_cpu, args.image_size)
-    S = O.num_style_coords(sd)
+def cpu_sample_sindices(S, n_coords):
     step = max(1, S // n_coords)
-    sind = list(range(0, S, step))[:n_coords]
-    t0 = time.perf_counter()
-    evals = 0
-    for _ in range(repeats):
-        O.attfind_sweep(sd, clf.classify_images, latents[:1], noise, sindices=sind,
-                        minmax_from=torch.stack([minmax[0], minmax[1]]))
-        evals += 2 * len(sind) + 1          # + the base image of the latent
-    dt = time.perf_counter() - t0
-    return evals / dt, dt, len(sind)
+    return list(range(0, S, step))[:n_coords]
+
+
+class CpuReference:
+    """The reference's CPU path on a bounded sample: `n_images` images x `n_coords` strided style coordinates x 2
+    directions, batch 1, one FULL generator forward + one classifier forward per coord-eval.
+
+    kind "reference": the unmodified reference files staged by oracle/make_ref.sh -- `attfind_extraction` of notebook
+    cell 5 exec'd verbatim (phase A included: encoder stand-in that returns the preset w, classifier, generator), the
+    reference `Generator` and `ResNet`/`MobileNet.classify_images`.  kind "port": oracle.stylex_oracle.attfind_sweep."""
+
+    def __init__(self, args, sd, model_cpu, noise):
+        import torch
+        from oracle import ref_loader as RL
+        from oracle import stylex_oracle as O
+        self.args, self.sd, self.noise = args, sd, noise
+        self.S = O.num_style_coords(sd)
+        self.kind = "reference" if RL.available() else "port"
+        self.O, self.RL = O, RL
+        if self.kind == "reference":
+            self.G = RL.reference_generator(sd, args.image_size)
+            self.clf = RL.reference_classifier(args.classifier, model_cpu, args.image_size)
+        else:
+            import stylex_b200 as sx
+            self.clf = sx.make_classifier(args.classifier, model_cpu, args.image_size)
+        g = torch.Generator().manual_seed(1234)
+        self.images = torch.rand(max(1, args.cpu_sample_images), 3, args.image_size, args.image_size, generator=g)
+
+    def describe(self, n_coords):
+        a = self.args
+        n_img = self.images.shape[0]
+        what = ("VERBATIM notebook cell 5 (attfind_extraction) over the reference Generator + classify_images"
+                if self.kind == "reference" else "oracle port of the notebook loop")
+        return (f"{what}: {n_img} image(s) x {n_coords} style coords (every {max(1, self.S // n_coords)}th) x 2 directions + "
+                f"{n_img} base image(s), batch-1 full forwards, {a.classifier}{'-18@224' if a.classifier == 'resnet' else 'V2'} fp32, "
+                f"{a.image_size}px")
+
+    def run(self, latents, n_coords):
+        """-> (coord-evals/s, seconds, coord-evals)"""
+        import torch
+        sind = cpu_sample_sindices(self.S, n_coords)
+        n_img = self.images.shape[0]
+        w = latents[:n_img, :512].clone()
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            calls = {"i": 0}
+
+            def encoder(batch):                      # stands in for stylex.encoder (NB:306): returns the preset w
+                i = calls["i"] % n_img
+                calls["i"] += 1
+                return w[i]
+            self.RL.run_reference_attfind(self.G, self.clf, self.images, encoder, self.noise, self.S, shift_size=1.0,
+                                          sindex_subset=sind, results_folder="mem://bench")
+        else:
+            lat = torch.cat([w, self.clf.classify_images(self.images)], dim=1)
+            self.O.attfind_sweep(self.sd, self.clf.classify_images, lat, self.noise, sindices=sind)
+        dt = time.perf_counter() - t0
+        evals = n_img * (2 * len(sind) + 1)
+        return evals / dt, dt, evals
+
+
+def calibrated_cpu_model(args, sd, model, noise):
+    """the seeded classifier calibrated on 8 generated images (CPU path of the --impl reference arm)."""
+    from stylex_b200 import synthetic
+    from oracle import stylex_oracle as O
+    import stylex_b200 as sx
+    L = len(O.generator_layout(sd))
+    lat = synthetic.make_latents(8, 42)
+    clf = sx.make_classifier(args.classifier, model, args.image_size)
+    calib = O.generator_forward(sd, O.styles_def_to_tensor([(lat, L)]), noise)
+    synthetic.calibrate_classifier(model, clf.preprocess, calib, chunk=8)
+    return model, lat
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (see CpuReference)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from stylex_b200 import synthetic
-    from oracle import stylex_oracle as O
 
     torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd, model, noise = build_workload(args.image_size, args.classifier)
-    L = len(O.generator_layout(sd))
-    lat = synthetic.make_latents(8, 42)
-    import stylex_b200 as sx
-    clf = sx.make_classifier(args.classifier, model, args.image_size)
-    calib = O.generator_forward(sd, O.styles_def_to_tensor([(lat, L)]), noise)
-    synthetic.calibrate_classifier(model, clf.preprocess, calib, chunk=8)
-    _, sc = O.generator_forward(sd, O.styles_def_to_tensor([(lat, L)]), noise, get_style_coords=True)
-    minmax = (sc.min(0).values, sc.max(0).values)
-    n_coords = max(2, args.cpu_sample_coords // 2)
+    model, lat = calibrated_cpu_model(args, sd, model, noise)
+    ref = CpuReference(args, sd, model, noise)
+    n_coords = max(2, args.cpu_sample_coords)
     for _ in range(args.warmup):
-        cpu_reference_rate(args, sd, model, noise, lat, minmax, 2)
+        ref.run(lat, 2)
     t0 = time.perf_counter()
     evals = 0
     for _ in range(args.steps):
-        r, dt, nc = cpu_reference_rate(args, sd, model, noise, lat, minmax, n_coords)
-        evals += 2 * nc + 1
+        _, _, n = ref.run(lat, n_coords)
+        evals += n
     dt = time.perf_counter() - t0
     value = evals / dt
-    sample = f"per step: 1 latent x {n_coords} style coords (every {O.num_style_coords(sd) // n_coords}th) x 2 directions + base image, batch 1"
+    sample = "per step: " + ref.describe(n_coords)
     emit({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"StylEx {args.image_size}px generator (S={O.num_style_coords(sd)}) + {args.classifier} classifier, AttFind sweep",
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric_name(args.image_size), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.image_size, ref.S, args.classifier), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    })
+    }, args)
+
+
+def workload_name(size, S, kind):
+    shape = {64: "CelebA-shaped", 256: "FFHQ-shaped"}.get(size, "")
+    clf = "ResNet-18@224" if kind == "resnet" else f"MobileNetV2@{size}"
+    return f"StylEx {size}px {shape} generator (capacity 16, S={S}) + {clf} 2-way classifier, random-init + calibrated; AttFind sweep"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_job(args, G, clf, noise, rank, world, dev, step_rate):
+    """ONE whole AttFind job through the public API, timed by the wall clock (max over ranks): pinned host latents -> H2D
+    -> `attfind_sweep(rank, world, gather=True)` (base images / logits / minima / maxima of ALL latents on every rank,
+    this rank's contiguous shard swept, ONE all-gather of the effects) -> `attfind_select` (class split + greedy top-k on
+    device, merged ranking) -> picks on the host.  `job-latents` per rank: 128 x 8 ranks = BASELINE config 3."""
+    import torch
+    import torch.distributed as dist
+    import stylex_b200 as sx
+    from stylex_b200 import synthetic
+
+    per_rank = args.job_latents or (128 if args.image_size >= 256 else 256)
+    n_total = per_rank * world
+    lat_pin = synthetic.make_latents(n_total, 4242).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t0 = time.perf_counter()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    lat = lat_pin.to(dev, non_blocking=True)
+    st = {}
+    res = sx.attfind_sweep(G, clf, lat, noise, precision=args.precision, max_batch=args.max_batch, rank=rank,
+                           world_size=world, gather=False, stats=st)
+    ev[1].record()
+    local = res["style_change"]
+    if world > 1:
+        from stylex_b200.dist import gather_effects
+        effects = gather_effects(local, n_total, world)
+    else:
+        effects = local
+    ev[2].record()
+    picks, merged, scores = sx.attfind_select(effects, res["base_prob"], 5, 0.5)      # syncs: picks come back to the host
+    ev[3].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], device=dev,
+                     dtype=torch.float64)
+    sig = torch.tensor([d * 100000 + s_ for c in (0, 1) for d, s_ in picks[c]] + [d * 100000 + s_ for d, s_ in merged] + [-1] * 10,
+                       device=dev, dtype=torch.int64)[:20]
+    agree = True
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sigs = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        agree = all(bool(torch.equal(sigs[0], x)) for x in sigs)
+    wall = float(t[0].item())
+    S = G.num_style_coords
+    evals = n_total * 2 * S
+    labels = torch.argmax(res["base_prob"], dim=1)
+    return {
+        "what": "whole job, wall clock, max over ranks: H2D latents -> base images/logits + minima/maxima of all latents -> "
+                "sharded sweep -> NCCL all-gather of effects -> class split + greedy top-5 per class on device -> merged picks on host",
+        "latents_total": n_total, "latents_per_rank": per_rank, "coord_evals": evals, "wall_s": wall,
+        "value": evals / wall, "unit": UNIT, "ratio_to_step_rate": (evals / wall) / step_rate if step_rate else None,
+        "sweep_ms": float(t[1].item()), "gather_ms": float(t[2].item()), "select_ms": float(t[3].item()),
+        "effects_bytes_gathered": int(effects.numel() * 4) if world > 1 else 0,
+        "class_sizes": [int((labels == 0).sum()), int((labels == 1).sum())],
+        "picks": {str(c): [list(p) for p in picks[c]] for c in (0, 1)}, "merged": [list(p) for p in merged],
+        "picks_agree_across_ranks": agree,
+    }
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -237,49 +371,12 @@ def run_ours(args):
     G.precision = args.precision
     synthetic.calibrate_classifier(clf.model, clf.preprocess, calib, chunk=8)
     model_cal_cpu = copy.deepcopy(clf.model).cpu().float()
-    if args.classifier_dtype == "bf16":
-        clf.set_compute(torch.bfloat16, channels_last=True)
-    else:
-        clf.set_compute(torch.float32, channels_last=True)
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
-
-    clf_mode = "eager"
-    if args.classifier_mode == "fused" and kind == "resnet":
-        try:  # validate the fused forward against the eager module on real generated images before trusting it
-            probe = calib[:8]
-            ref_logits = clf.classify_images(probe)
-            clf.fuse_for_inference()
-            if args.stem == "s2d":
-                clf.fused.enable_s2d_stem()
-            if args.maxpool == "native":
-                clf.fused.enable_native_pool()
-            got = clf.classify_images(probe)
-            torch.cuda.synchronize()
-            tol = 0.05 * float(ref_logits.abs().max()) + 0.05
-            if not torch.isfinite(got).all() or float((got - ref_logits).abs().max()) > tol:
-                raise RuntimeError(f"fused classifier deviates: {float((got - ref_logits).abs().max()):.3e} > {tol:.3e}")
-            clf_mode = ("fused (BN folded, aten::cudnn_convolution_[add_]relu" + (", 7x7/2 stem as 4x4/1 on space-to-depth input" if args.stem == "s2d" else "")
-                        + (", native 3x3/2 max-pool)" if args.maxpool == "native" else ")"))
-        except Exception as e:  # noqa: BLE001 -- any failure means: keep the eager module, say so in the JSON
-            clf.fused = None
-            clf_mode = f"eager (fused path unavailable: {type(e).__name__}: {str(e)[:120]})"
-
-    pre_mode = "torch (resize, sub, div, cast, permute)"
-    if args.preprocess == "native" and kind == "resnet":
-        try:
-            probe = calib[:8]
-            ref_logits = clf.classify_images(probe)
-            clf.use_native_preprocess(True)
-            got = clf.classify_images(probe)
-            torch.cuda.synchronize()
-            tol = 0.03 * float(ref_logits.abs().max()) + 0.03
-            if not torch.isfinite(got).all() or float((got - ref_logits).abs().max()) > tol:
-                raise RuntimeError(f"native preprocess deviates: {float((got - ref_logits).abs().max()):.3e} > {tol:.3e}")
-            pre_mode = "native (sx_resize_aa_normalize: antialiased resize + normalise + cast + NHWC in one kernel)"
-        except Exception as e:  # noqa: BLE001
-            clf.native_preprocess = False
-            pre_mode = f"torch (native preprocess unavailable: {type(e).__name__}: {str(e)[:120]})"
+    # validated against the eager module on real generated images before it is trusted (classifiers.configure_throughput)
+    info = clf.configure_throughput(calib[:8], dtype=torch.bfloat16 if args.classifier_dtype == "bf16" else torch.float32,
+                                    fused=args.classifier_mode == "fused", stem=args.stem, maxpool=args.maxpool,
+                                    preprocess=args.preprocess)
+    clf_mode, pre_mode = info["classifier_mode"], info["preprocess"]
+    clf_inner = clf
 
     class TimedClassifier:
         """records CUDA events around every classifier call so the step breakdown can name the PyTorch share."""
@@ -394,6 +491,11 @@ def run_ours(args):
         e2e = {"value": float(tot2.item()) / (float(t2.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(lps * 514 * 4 + size * size * 4), "d2h_bytes_per_step": int(lps * 2 * S * 2 * 4)}
 
+    # ---------------- whole job: host latents -> sweep -> all-gather -> selection -> picks (wall clock) ----------------
+    job = None
+    if not args.no_job:
+        job = run_job(args, G, clf_inner, noise, rank, world, dev, value)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -442,25 +544,25 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         torch.backends.cudnn.allow_tf32 = False
-        rate, dt, nc = cpu_reference_rate(args, sd, model_cal_cpu, noise_cpu, lat_all, (minima.cpu(), maxima.cpu()),
-                                          args.cpu_sample_coords)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 latent x {nc} style coords (every {S // nc}th) x 2 directions + base image, batch-1 full forwards, {dt:.1f} s"}
+        ref = CpuReference(args, sd, model_cal_cpu, noise_cpu)
+        ref.run(lat_all, 2)                                                    # warm-up (thread pools, oneDNN primitives)
+        rate, dt, _ = ref.run(lat_all, max(2, args.cpu_sample_coords))
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": ref.kind,
+               "sample": ref.describe(max(2, args.cpu_sample_coords)) + f", {dt:.1f} s"}
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(size), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": f"StylEx {size}px FFHQ-shaped generator (capacity 16, S={S}) + {kind}-18@224 classifier; "
-                               f"AttFind sweep, {lps} latent(s)/rank/step x {S} coords x 2 directions",
+        "config": {"workload": workload_name(size, S, kind) + f", {lps} latent(s)/rank/step x {S} coords x 2 directions",
                    "coord_evals_per_step": int(2 * S * lps * world), "max_batch": args.max_batch,
                    "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)", "classifier_mode": clf_mode, "classifier_preprocess": pre_mode,
                    "prefix_reuse": True, "l2": f"inputs larger than L2: every {args.max_batch}-eval batch streams >{args.max_batch * 16.8e6 / 1e9:.1f} GB of activations (L2 = 126 MB)",
                    "pool_latents": pool_n, "parallelism": f"latent-sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roofline, "cpu_baseline": cpu,
-        "conv_flops_per_full_image": conv_flops_per_image(plan.pairs),
+        "job": job, "conv_flops_per_full_image": conv_flops_per_image(plan.pairs),
     }
-    emit(out)
+    emit(out, args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -475,10 +577,13 @@ def _claim_stdout():
     os.dup2(2, 1)
 
 
-def emit(obj):
+def emit(obj, args=None):
     line = (json.dumps(obj) + "\n").encode()
     sys.stdout.flush()
     os.write(_REAL_STDOUT, line)
+    if args is not None and getattr(args, "out", None):
+        with open(args.out, "ab") as f:
+            f.write(line)
 
 
 if __name__ == "__main__":

@@ -123,11 +123,23 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"stylex_b200 native call {what} failed (code {rc}): {msg}")
 
 
-def require_cuda(*tensors: torch.Tensor) -> None:
+def require_cuda(*tensors: torch.Tensor, same_device: bool = True) -> None:
+    """Every native call launches on the CURRENT device's current stream (``stream_ptr``): the tensors it is handed must
+    live on that device -- a tensor of another GPU would be dereferenced from the wrong context.  Callers that take a
+    reference-style ``cuda_rank`` / ``rank`` argument (``attfind_extraction``, ``StylEx``) make that device current
+    themselves; anything else raises here instead of faulting on the device."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("stylex_b200 ops run on CUDA tensors only (there is no CPU fallback); got a "
                                f"{t.device} tensor")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if same_device and t.device.index != cur:
+            raise RuntimeError(f"stylex_b200 native call: tensor on {t.device} but the current CUDA device is cuda:{cur}; "
+                               f"wrap the call in `with torch.cuda.device({t.device.index})` (or torch.cuda.set_device)")
 
 
 def stream_ptr() -> int:

@@ -85,7 +85,8 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
                   precision: Optional[str] = None, max_batch: int = 128, rank: int = 0, world_size: int = 1,
                   sindices: Optional[Sequence[int]] = None, image_indices: Optional[Sequence[int]] = None,
                   gather: bool = True, stats: Optional[dict] = None,
-                  minmax: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                  minmax: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                  zero_row: bool = False) -> Dict[str, torch.Tensor]:
     """Phases A(second half)-C of ``attfind_extraction`` (NB:316-389) for latents ``[N, latent]``.
 
     Every rank computes the style coordinates, base images and base logits of ALL N latents (cheap, and it
@@ -97,7 +98,9 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     ``sindices`` / ``image_indices`` restrict the sweep to a subset (bounded benchmark / test samples);
     untouched entries of 'style_change' stay 0.  ``minmax`` = (minima, maxima) [S] supplies the global
     per-coordinate extrema when ``latents`` is only a slice of the job (they must come from ALL latents,
-    NB:340); by default they are computed from ``latents``.
+    NB:340); by default they are computed from ``latents``.  ``zero_row``: an all-zero style row takes part in the
+    extrema -- what the notebook computes when fewer images pass the discriminator filter than ``num_images`` (its
+    ``style_coordinates`` buffer keeps zero rows for the images it never found, and NB:340 reduces over the whole buffer).
     """
     precision = precision or G.precision
     N.require_cuda(latents, noise)
@@ -124,6 +127,9 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
         maxima = torch.empty_like(minima)
         N.check(lib.sx_attfind_minmax(styles_all.data_ptr(), n_all, S, row, minima.data_ptr(), maxima.data_ptr(), stream),
                 "sx_attfind_minmax")                                                    # NB:340
+        if zero_row:
+            minima.clamp_(max=0.0)
+            maxima.clamp_(min=0.0)
     else:
         minima, maxima = (N.f32c(t) for t in minmax)
         N.require_cuda(minima, maxima)
@@ -269,6 +275,15 @@ def attfind_extraction(dataloader, num_images, results_folder, stylex, classifie
     if batch_size != 1:
         raise ValueError('Please use a batch_size equal to 1')                          # NB:284-285
     dev = torch.device("cuda", cuda_rank)
+    with torch.cuda.device(dev):      # native launches go to the CURRENT device's stream: make cuda_rank current
+        return _attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, noise, num_style_coords,
+                                   shift_size, discriminator_threshold, image_size, dev, use_discriminator,
+                                   use_old_architecture, precision, max_batch, rank, world_size, front_batch)
+
+
+def _attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, noise, num_style_coords, shift_size,
+                        discriminator_threshold, image_size, dev, use_discriminator, use_old_architecture, precision,
+                        max_batch, rank, world_size, front_batch):
     G = stylex.G
     if num_style_coords != G.num_style_coords:
         raise ValueError(f"num_style_coords={num_style_coords} but the generator has {G.num_style_coords} (quirk Q5)")
@@ -299,7 +314,10 @@ def attfind_extraction(dataloader, num_images, results_folder, stylex, classifie
                            discriminator=have_d)
         keep = torch.ones(x.shape[0], dtype=torch.bool, device=dev)
         if use_discriminator and discriminator_threshold is not None:
-            keep = ~(fe["discriminator"][:, 0] < discriminator_threshold)                # NB:262-266: skip when output < threshold
+            # NB:262-266 returns (False, out) when out < threshold and (True, out) otherwise; NB:323,327 bind that flag to
+            # `skip` and `continue` when it is set: the executed reference KEEPS the images with out < threshold (pinned by
+            # tests/golden/frontend_filter.npz, the verbatim loop run with use_discriminator=True)
+            keep = fe["discriminator"][:, 0] < discriminator_threshold
         idx = keep.nonzero().flatten()[: num_images - images_found]
         k = int(idx.numel())
         original_images[images_found: images_found + k] = x[idx]
@@ -309,8 +327,9 @@ def attfind_extraction(dataloader, num_images, results_folder, stylex, classifie
         images_found += k
     if images_found == 0:
         raise ValueError('No images pass the threshold check')
+    # fewer images than asked for: the notebook's unfilled (zero) rows take part in its min / max (NB:291, 340)
     res = attfind_sweep(G, classifier, image_latents[:images_found], noise, shift_size=shift_size, precision=precision,
-                        max_batch=max_batch, rank=rank, world_size=world_size)
+                        max_batch=max_batch, rank=rank, world_size=world_size, zero_row=images_found < num_images)
     out = {
         "style_change": _pad(res["style_change"], num_images), "latents": image_latents,
         "base_prob": _pad(res["base_prob"], num_images), "minima": res["minima"][None], "maxima": res["maxima"][None],
@@ -358,7 +377,13 @@ def load_records(path: str, threshold_index: Optional[int] = None) -> Dict[str, 
             import h5py
         except ImportError:
             from . import hdf5_lite
-            allv = hdf5_lite.read_hdf5(path)
+            skipped: Dict[str, str] = {}
+            allv = hdf5_lite.read_hdf5(path, skipped)
+            missing = [k for k in DATASET_NAMES if k not in allv]
+            if missing:
+                why = "; ".join(f"'{k}': {skipped.get(k, 'not in the file')}" for k in missing)
+                raise ValueError(f"{path}: the built-in HDF5 reader (h5py is not installed) cannot provide {why}. It parses "
+                                 "contiguous / compact datasets only -- install h5py to read chunked or compressed records.")
             raw = {k: allv[k] for k in DATASET_NAMES}
         else:
             with h5py.File(path, "r") as f:

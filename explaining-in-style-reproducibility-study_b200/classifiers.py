@@ -86,6 +86,57 @@ class _Wrapper:
         self.native_preprocess = on
         return self
 
+    def configure_throughput(self, probe: torch.Tensor, dtype: torch.dtype = torch.bfloat16, fused: bool = True,
+                             stem: str = "s2d", maxpool: str = "native", preprocess: str = "native",
+                             tol_rel: float = 0.05, tol_abs: float = 0.05):
+        """The AttFind throughput configuration of the PyTorch classifier (what ``bench.py`` measures), in one place:
+        ``dtype`` + channels_last, then -- each validated on ``probe`` (real generated images) against the logits of the
+        module as it stood before the switch, and rolled back when it deviates by more than ``tol_rel * max|logit| +
+        tol_abs`` -- BatchNorm folding + fused cuDNN conv ops, the space-to-depth stem, the native max-pool and the
+        native one-pass preprocessing.  fp32 turns TF32 off (parity mode).  Returns {"classifier_mode", "preprocess"}
+        describing what is active."""
+        self.set_compute(dtype, channels_last=True)
+        if dtype == torch.float32:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+
+        def deviates(ref, got):
+            tol = tol_rel * float(ref.abs().max()) + tol_abs
+            err = float((got - ref).abs().max()) if torch.isfinite(got).all() else float("inf")
+            return err > tol, err, tol
+
+        mode = "eager"
+        if fused and self.kind == "resnet":
+            try:
+                ref = self.classify_images(probe)
+                self.fuse_for_inference()
+                if stem == "s2d":
+                    self.fused.enable_s2d_stem()
+                if maxpool == "native":
+                    self.fused.enable_native_pool()
+                bad, err, tol = deviates(ref, self.classify_images(probe))
+                if bad:
+                    raise RuntimeError(f"fused classifier deviates: {err:.3e} > {tol:.3e}")
+                mode = ("fused (BN folded, aten::cudnn_convolution_[add_]relu"
+                        + (", 7x7/2 stem as 4x4/1 on space-to-depth input" if stem == "s2d" else "")
+                        + (", native 3x3/2 max-pool)" if maxpool == "native" else ")"))
+            except Exception as e:  # noqa: BLE001 -- any failure means: keep the eager module, and say so
+                self.fused = None
+                mode = f"eager (fused path unavailable: {type(e).__name__}: {str(e)[:120]})"
+        pre = "torch (resize, sub, div, cast, permute)"
+        if preprocess == "native" and self.kind == "resnet":
+            try:
+                ref = self.classify_images(probe)
+                self.use_native_preprocess(True)
+                bad, err, tol = deviates(ref, self.classify_images(probe))
+                if bad:
+                    raise RuntimeError(f"native preprocess deviates: {err:.3e} > {tol:.3e}")
+                pre = "native (sx_resize_aa_normalize: antialiased resize + normalise + cast + NHWC in one kernel)"
+            except Exception as e:  # noqa: BLE001
+                self.native_preprocess = False
+                pre = f"torch (native preprocess unavailable: {type(e).__name__}: {str(e)[:120]})"
+        return {"classifier_mode": mode, "preprocess": pre}
+
     def _native_pre(self, images: torch.Tensor, s2d: bool = False) -> torch.Tensor:
         import ctypes
         from . import _native as N

@@ -230,8 +230,10 @@ class _File:
         return out
 
 
-def read_hdf5(path: str) -> Dict[str, np.ndarray]:
-    """Read every contiguous / compact numeric dataset of the root group (other objects are skipped)."""
+def read_hdf5(path: str, skipped: Dict[str, str] = None) -> Dict[str, np.ndarray]:
+    """Read every contiguous / compact numeric dataset of the root group.  Objects this reader does not parse (chunked or
+    compressed datasets, non-numeric types, sub-groups) are left out and, when ``skipped`` is a dict, recorded there as
+    ``{name: reason}`` so that callers can say WHY a dataset they need is absent."""
     f = _File(open(path, "rb").read())
     _, root_hdr, cache, _ = struct.unpack("<QQII", f.root_entry[:24])
     btree = heap = None
@@ -255,13 +257,19 @@ def read_hdf5(path: str) -> Dict[str, np.ndarray]:
                     dtype = _parse_datatype(data)
                 elif mtype == 0x0008:
                     layout = data
-        except (TypeError, ValueError):
+        except (TypeError, ValueError) as e:
+            if skipped is not None:
+                skipped[name] = f"unsupported object header ({e})"
             continue
         if shape is None or dtype is None or layout is None or layout[0] not in (1, 2, 3):
+            if skipped is not None:
+                skipped[name] = "not a numeric dataset with a version 1-3 data-layout message (a sub-group?)"
             continue
         count = int(np.prod(shape)) if shape else 1
         if layout[0] in (1, 2):                           # layout versions 1 / 2 (older libraries): class at byte 2
             if layout[2] != 1:
+                if skipped is not None:
+                    skipped[name] = "chunked / external storage (layout class %d)" % layout[2]
                 continue
             addr = struct.unpack("<Q", layout[8:16])[0]
             raw = f.at(addr, count * dtype.itemsize) if count and addr != UNDEF else b""
@@ -271,8 +279,10 @@ def read_hdf5(path: str) -> Dict[str, np.ndarray]:
         elif layout[1] == 0:                              # compact
             size = struct.unpack("<H", layout[2:4])[0]
             raw = layout[4:4 + size]
-        else:
-            continue                                      # chunked: not needed for the AttFind records
+        else:                                             # chunked (what compression / resizable datasets use)
+            if skipped is not None:
+                skipped[name] = "chunked storage (layout class %d): written with chunks= / compression=" % layout[1]
+            continue
         if len(raw) < count * dtype.itemsize:
             out[name] = np.zeros(shape, dtype)            # never written: the fill value (zero)
         else:

@@ -444,12 +444,13 @@ class GeneratorPlan:
     def sync(self):
         """(re)pack the weights when the module's parameters changed (load_state_dict, .to(), optimiser step)."""
         ps = self._param_list()
-        N.require_cuda(*ps)
+        N.require_cuda(*ps, same_device=False)      # packing runs under the parameters' own device (below)
         versions = tuple((p.data_ptr(), p._version) for p in ps)
         if versions == self._versions:
             return
-        N.device_check()
         dev = ps[0].device
+        with torch.cuda.device(dev):
+            N.device_check()
         keep = [N.f32c(p.detach()) for p in ps]
         blocks = (N.sx_block_params * len(self.G.blocks))()
         names = [f[0] for f in N.sx_block_params._fields_]
@@ -550,6 +551,13 @@ class Generator(nn.Module):
     @property
     def num_style_coords(self):
         return sum(b.num_style_coords for b in self.blocks)
+
+    def __getstate__(self):
+        """copy.deepcopy / torch.save(model): the native plan (a ctypes handle + device workspaces) is not part of the
+        module's state; the copy rebuilds it lazily on its first forward."""
+        state = self.__dict__.copy()
+        state["_plan"] = None
+        return state
 
     def plan(self) -> GeneratorPlan:
         if self._plan is None:

@@ -28,7 +28,22 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("STYLEX_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.sh (git-ignored copy)
+
+
+def _find_root() -> str:
+    """The reference checkout: $STYLEX_REFERENCE_ROOT, else /root/reference (build container), else the files
+    ``oracle/make_ref.sh`` staged under ``oracle/_ref`` (the GPU box, where /root/reference does not exist)."""
+    env = os.environ.get("STYLEX_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(root, "stylex", "stylex_train.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _R = None
 
 
@@ -156,8 +171,11 @@ class _MemFile:
         pass
 
 
-def notebook_namespace(use_old_architecture=True):
-    """exec NB cells 5, 11 and 15 verbatim (attfind_extraction, find_significant_styles, helpers)."""
+def notebook_namespace(use_old_architecture=True, sindex_subset=None):
+    """exec NB cells 5, 11 and 15 verbatim (attfind_extraction, find_significant_styles, helpers).
+
+    ``sindex_subset``: bounded samples only -- the notebook wraps its style-coordinate loop in ``tqdm.tqdm`` (NB:356);
+    the progress-bar stand-in injected here then yields just these coordinates.  The cell itself stays verbatim."""
     R = load_reference()
     nb = json.load(open(os.path.join(REFERENCE_ROOT, "stylex", "run_attfind_combined.ipynb")))
     h5 = types.ModuleType("h5py")
@@ -166,6 +184,9 @@ def notebook_namespace(use_old_architecture=True):
     class _tqdm_mod:
         @staticmethod
         def tqdm(x, *a, **k):
+            if sindex_subset is not None and isinstance(x, range):
+                keep = set(int(s) for s in sindex_subset)
+                return [s for s in x if s in keep]
             return x
 
     ns = {
@@ -203,14 +224,21 @@ class FakeStylEx:
 
 
 def run_reference_attfind(G, classifier, images, encoder, noise, num_style_coords, shift_size=1.0,
-                          discriminator=None, results_folder="mem://attfind"):
-    """Run the VERBATIM notebook ``attfind_extraction`` (NB:269-417) on CPU; returns the 9 datasets."""
-    ns = notebook_namespace(True)
+                          discriminator=None, results_folder="mem://attfind", sindex_subset=None,
+                          use_discriminator=False, discriminator_threshold=-0.5, num_images=None, extra_tail=True):
+    """Run the VERBATIM notebook ``attfind_extraction`` (NB:269-417) on CPU; returns the 9 datasets.
+    ``sindex_subset`` bounds the coordinate loop (see ``notebook_namespace``); untouched effect entries are whatever
+    ``torch.Tensor(1, 2, S, 2)`` held (uninitialised, NB:354) -- callers of a bounded run must only read the subset.
+    ``num_images`` < len(images) together with ``use_discriminator`` exercises the filter (NB:322-327)."""
+    ns = notebook_namespace(True, sindex_subset=sindex_subset)
     stylex = FakeStylEx(G, encoder, discriminator if discriminator is not None else (lambda img: torch.zeros(1)))
-    loader = [images[i: i + 1] for i in range(images.shape[0])] + [images[:1]]   # NB:300 reads one past the end
+    loader = [images[i: i + 1] for i in range(images.shape[0])]
+    if extra_tail:
+        loader = loader + [images[:1]]                                           # NB:300 reads one past the end
     with cpu_cuda_identity(), torch.no_grad():
-        ns["attfind_extraction"](loader, images.shape[0], results_folder, stylex, classifier, None, noise,
-                                 num_style_coords, shift_size, -0.5, image_size=images.shape[-1], batch_size=1,
-                                 cuda_rank=0, use_discriminator=False)
+        ns["attfind_extraction"](loader, images.shape[0] if num_images is None else num_images, results_folder, stylex,
+                                 classifier, None, noise, num_style_coords, shift_size, discriminator_threshold,
+                                 image_size=images.shape[-1], batch_size=1, cuda_rank=0,
+                                 use_discriminator=use_discriminator)
     d = _MemFile.store[os.path.join(results_folder, "style_change_records.hdf5")]
     return {k: np.array(v.arr) for k, v in d.items()}

@@ -627,14 +627,33 @@ def test_attfind_extraction_phase_a_matches_verbatim_notebook(dev, golden, tmp_p
         assert float((out[k].cpu() - ref).abs().max()) <= FP32_TOL, k
     tot = float(out["style_change"].abs().sum())
     assert abs(tot - float(z["nb.style_change_abs_sum"])) <= 1e-3 * float(z["nb.style_change_abs_sum"])
-    # the discriminator filter (NB:262-266, 327-328): images whose output is below the threshold are skipped, order kept
-    d = z["nb.discriminator"][:, 0]
-    thr = float(np.sort(d)[2]) - 1e-3                                   # keeps the 3 highest
-    want = [i for i in range(n) if not d[i] < thr]
-    out2 = sx.attfind_extraction(images, len(want), None, st, clf, None, noise, st.G.num_style_coords, 1.0, thr,
-                                 image_size=size, use_discriminator=True, front_batch=2)
-    assert float((out2["latents"].cpu() - torch.from_numpy(z["nb.latents"][want])).abs().max()) <= FP32_TOL
-    assert float((out2["discriminator"].cpu()[:, 0] - torch.from_numpy(d[want])).abs().max()) <= FP32_TOL
+
+
+def test_attfind_extraction_discriminator_filter_matches_verbatim_notebook(dev, golden):
+    """``use_discriminator=True`` against the VERBATIM notebook loop (tests/golden/frontend_filter.npz): the executed
+    reference keeps the images whose discriminator output is BELOW the threshold (NB:262-266 returns the flag that NB:327
+    reads as `skip`), in dataloader order; and when fewer images pass than ``num_images`` its zero rows take part in
+    minima / maxima (NB:291, 340), which changes every shift."""
+    z = golden("frontend_small.npz")
+    f = golden("frontend_filter.npz")
+    size, st, clf = _frontend(z, dev)
+    images = [torch.from_numpy(z["images"][i: i + 1]) for i in range(z["images"].shape[0])]
+    noise = torch.from_numpy(z["noise"]).to(dev)
+    thr = float(f["threshold"])
+    d = f["d_all"]
+    want = [i for i in range(len(images)) if d[i] < thr]
+    assert len(want) == 3
+    for tag, num_images, loader in (("exact", 3, images + images[:1]), ("short", 4, images)):
+        out = sx.attfind_extraction(loader, num_images, None, st, clf, None, noise, st.G.num_style_coords, 1.0, thr,
+                                    image_size=size, use_discriminator=True, front_batch=2)
+        for k in ("latents", "base_prob", "style_coordinates", "discriminator", "original_images", "minima", "maxima"):
+            ref = torch.from_numpy(f[f"{tag}.{k}"])
+            assert out[k].shape == ref.shape, (tag, k)
+            assert float((out[k].cpu() - ref).abs().max()) <= FP32_TOL, (tag, k)
+        assert float((out["latents"].cpu()[:3] - torch.from_numpy(z["nb.latents"][want])).abs().max()) <= FP32_TOL
+        ref = torch.from_numpy(f[f"{tag}.style_change"])
+        err = float((out["style_change"].cpu() - ref).abs().max())
+        assert err <= 2e-4 * max(1.0, float(ref.abs().max())), (tag, err)
 
 
 def test_stylex_container_checkpoint_on_device(dev, tmp_path):

@@ -434,3 +434,81 @@ def test_find_discriminator_threshold_host_logic(tmp_path):
     assert np.array_equal(back["generated_images"], res["generated_images"].numpy())
     with pytest.raises(StopIteration):
         sx.find_discriminator_threshold(st, Clf(), images[:3], 5, None, image_size=4, noise=noise)
+
+
+def test_generator_deepcopy_and_pickle_after_plan_creation():
+    """the native plan (ctypes handle) must not make copy.deepcopy / torch.save(model) fail; the copy
+    rebuilds its own plan lazily."""
+    import copy
+    import io
+    import stylex_b200 as sx
+    G = sx.Generator(16, 514, network_capacity=4)
+    plan = G.plan()                        # host-only: creates the native handle, no CUDA call
+    assert plan.S == G.num_style_coords
+    G2 = copy.deepcopy(G)
+    assert G2._plan is None and G._plan is plan
+    assert G2.plan() is not plan and G2.plan().S == plan.S
+    buf = io.BytesIO()
+    torch.save(G, buf)
+    buf.seek(0)
+    G3 = torch.load(buf, weights_only=False)
+    assert G3._plan is None and torch.equal(G3.initial_block, G.initial_block)
+
+
+def test_load_records_names_unreadable_datasets(tmp_path):
+    """a record file whose datasets the built-in reader cannot parse gives a clear error, not a KeyError."""
+    from stylex_b200 import attfind, hdf5_lite
+    try:
+        import h5py  # noqa: F401
+        pytest.skip("h5py present: load_records goes through libhdf5")
+    except ImportError:
+        pass
+    arrays = {k: np.zeros((2, 3), np.float32) for k in attfind.DATASET_NAMES if k != "style_change"}
+    path = str(tmp_path / "style_change_records.hdf5")
+    hdf5_lite.write_hdf5(path, arrays)
+    with pytest.raises(ValueError, match="style_change"):
+        attfind.load_records(path)
+
+
+def test_selection_margin_report_replays_the_oracle_selection():
+    """tests/helpers.selection_margin_report (used by the top-k parity tests and profiles/topk_parity.py) follows exactly
+    the picks of the oracle's find_significant_styles, and flags a perturbation larger than the margins."""
+    from oracle import stylex_oracle as O
+    from helpers import selection_margin_report
+    rng = np.random.default_rng(3)
+    eff = (rng.normal(size=(30, 2, 40, 2)) * 0.6).astype(np.float32)
+    base = rng.normal(size=(30, 2)).astype(np.float32)
+    picks, _, _ = O.attfind_select(eff, base, 5, 0.5)
+    rep = selection_margin_report(eff, base, eff + 1e-7, base, k=5, max_image_effect=2.5)
+    for c in (0, 1):
+        assert [tuple(r["pick"]) for r in rep["classes"][str(c)]] == picks[c]
+    assert rep["picks_provably_equal"]
+    noisy = eff + (rng.normal(size=eff.shape) * 0.5).astype(np.float32)
+    assert not selection_margin_report(eff, base, noisy, base)["picks_provably_equal"]
+
+
+def test_reference_arm_runs_the_staged_reference(tmp_path):
+    """`oracle/make_ref.sh` stages the unmodified reference files under oracle/_ref and the loader
+    finds them there when /root/reference is absent (the GPU box): the VERBATIM notebook cell then runs from the copy."""
+    import subprocess
+    import sys
+    staged = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isfile(os.path.join(staged, "stylex", "stylex_train.py")):
+        pytest.skip("oracle/_ref not staged (run oracle/make_ref.sh where /root/reference exists)")
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from oracle import ref_loader as RL\n"
+        "from stylex_b200 import synthetic\n"
+        "assert RL.REFERENCE_ROOT == %r, RL.REFERENCE_ROOT\n"
+        "sd = synthetic.make_generator_state(16, seed=1, network_capacity=4)\n"
+        "G = RL.reference_generator(sd, 16, network_capacity=4)\n"
+        "clf = RL.reference_classifier('mobilenet', torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(768, 2)), 16)\n"
+        "w = torch.randn(2, 512)\n"
+        "calls = [0]\n"
+        "def enc(b):\n"
+        "    calls[0] += 1; return w[(calls[0] - 1) %% 2]\n"
+        "res = RL.run_reference_attfind(G, clf, torch.rand(2, 3, 16, 16), enc, synthetic.make_noise(16, 1), 136, sindex_subset=[0, 50, 135])\n"
+        "print('OK', res['style_change'].shape, float(abs(res['style_change'][:, :, [0, 50, 135]]).max()))\n" % (ROOT, staged))
+    env = dict(os.environ, STYLEX_REFERENCE_ROOT=staged)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "OK (2, 2, 136, 2)" in r.stdout, r.stdout + r.stderr
