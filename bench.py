@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-job", action="store_true", help="skip the whole-job leg")
+    ap.add_argument("--no-verify", action="store_true", help="whole-job leg without the fp32 verification of the top-k candidates")
     ap.add_argument("--job-latents", type=int, default=0,
                     help="latents PER RANK of the whole-job leg (default: 128 at 256px = config 3 on 8 ranks; 256 at 64px = config 2)")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
@@ -272,11 +273,13 @@ def workload_name(size, S, kind):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def run_job(args, G, clf, noise, rank, world, dev, step_rate):
+def run_job(args, G, clf, clf_exact, noise, rank, world, dev, step_rate):
     """ONE whole AttFind job through the public API, timed by the wall clock (max over ranks): pinned host latents -> H2D
-    -> `attfind_sweep(rank, world, gather=True)` (base images / logits / minima / maxima of ALL latents on every rank,
-    this rank's contiguous shard swept, ONE all-gather of the effects) -> `attfind_select` (class split + greedy top-k on
-    device, merged ranking) -> picks on the host.  `job-latents` per rank: 128 x 8 ranks = BASELINE config 3."""
+    -> `attfind_sweep(rank, world)` in the throughput mode (base images / logits / minima / maxima of ALL latents on every
+    rank, this rank's contiguous shard swept) -> ONE all-gather of the effects -> `attfind_verify_topk` (the candidate
+    columns re-evaluated in the parity mode, sharded the same way, so that the picks are the reference's exact top-k) ->
+    class split + greedy top-k on device, merged ranking -> picks on the host.
+    `job-latents` per rank: 128 x 8 ranks = BASELINE config 3; 256 x 1 at 64px = config 2."""
     import torch
     import torch.distributed as dist
     import stylex_b200 as sx
@@ -293,7 +296,7 @@ def run_job(args, G, clf, noise, rank, world, dev, step_rate):
 
     barrier()
     t0 = time.perf_counter()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
     lat = lat_pin.to(dev, non_blocking=True)
     st = {}
@@ -306,13 +309,20 @@ def run_job(args, G, clf, noise, rank, world, dev, step_rate):
         effects = gather_effects(local, n_total, world)
     else:
         effects = local
+    res["style_change"] = effects
     ev[2].record()
-    picks, merged, scores = sx.attfind_select(effects, res["base_prob"], 5, 0.5)      # syncs: picks come back to the host
+    fast = sx.attfind_select(effects, res["base_prob"], 5, 0.5)                    # what the throughput mode alone would pick
     ev[3].record()
+    if args.no_verify:
+        picks, merged, scores = fast
+        vinfo = None
+    else:
+        picks, merged, scores, vinfo = sx.attfind_verify_topk(G, clf_exact, lat, noise, res, 5, 0.5, precision="fp32",
+                                                              max_batch=128, rank=rank, world_size=world)
+    ev[4].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    t = torch.tensor([wall, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], device=dev,
-                     dtype=torch.float64)
+    t = torch.tensor([wall] + [ev[i].elapsed_time(ev[i + 1]) for i in range(4)], device=dev, dtype=torch.float64)
     sig = torch.tensor([d * 100000 + s_ for c in (0, 1) for d, s_ in picks[c]] + [d * 100000 + s_ for d, s_ in merged] + [-1] * 10,
                        device=dev, dtype=torch.int64)[:20]
     agree = True
@@ -325,17 +335,25 @@ def run_job(args, G, clf, noise, rank, world, dev, step_rate):
     S = G.num_style_coords
     evals = n_total * 2 * S
     labels = torch.argmax(res["base_prob"], dim=1)
-    return {
-        "what": "whole job, wall clock, max over ranks: H2D latents -> base images/logits + minima/maxima of all latents -> "
-                "sharded sweep -> NCCL all-gather of effects -> class split + greedy top-5 per class on device -> merged picks on host",
+    out = {
+        "what": "whole job, wall clock, max over ranks: H2D latents -> base images/logits + minima/maxima of all latents -> sharded "
+                "bf16 sweep -> NCCL all-gather of effects -> top-k candidates re-evaluated in fp32 (sharded, small all-gathers) -> "
+                "class split + greedy top-5 per class on device -> merged picks on host",
         "latents_total": n_total, "latents_per_rank": per_rank, "coord_evals": evals, "wall_s": wall,
         "value": evals / wall, "unit": UNIT, "ratio_to_step_rate": (evals / wall) / step_rate if step_rate else None,
         "sweep_ms": float(t[1].item()), "gather_ms": float(t[2].item()), "select_ms": float(t[3].item()),
+        "verify_ms": float(t[4].item()),
         "effects_bytes_gathered": int(effects.numel() * 4) if world > 1 else 0,
         "class_sizes": [int((labels == 0).sum()), int((labels == 1).sum())],
         "picks": {str(c): [list(p) for p in picks[c]] for c in (0, 1)}, "merged": [list(p) for p in merged],
         "picks_agree_across_ranks": agree,
+        "throughput_mode_picks": {str(c): [list(p) for p in fast[0][c]] for c in (0, 1)},
+        "throughput_mode_picks_equal_exact": fast[0] == picks and fast[1] == merged,
     }
+    if vinfo is not None:
+        out["verify"] = {k: v for k, v in vinfo.items() if k not in ("style_change", "base_prob")}
+        out["verify"]["exact_fraction_of_coord_evals"] = vinfo["exact_evals"] / evals
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -354,6 +372,8 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     _native.device_check()
     torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False          # fp32 work (calibration, the parity-mode verification) is real fp32;
+    torch.backends.cuda.matmul.allow_tf32 = False    # the bf16 throughput classifier is not affected
     size, kind = args.image_size, args.classifier
     sd, model_cpu, noise_cpu = build_workload(size, kind)
     G = sx.Generator(size, 514).to(dev)
@@ -494,7 +514,8 @@ def run_ours(args):
     # ---------------- whole job: host latents -> sweep -> all-gather -> selection -> picks (wall clock) ----------------
     job = None
     if not args.no_job:
-        job = run_job(args, G, clf_inner, noise, rank, world, dev, value)
+        clf_exact = sx.make_classifier(kind, copy.deepcopy(model_cal_cpu).to(dev), size)      # parity mode: fp32 eager
+        job = run_job(args, G, clf_inner, clf_exact, noise, rank, world, dev, value)
 
     if rank != 0:
         if world > 1:

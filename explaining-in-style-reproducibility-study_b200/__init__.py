@@ -12,7 +12,7 @@ from . import _native  # noqa: F401
 from .modules import (Blur, Conv2DMod, Conv2DModFunction, Generator, GeneratorBlock, GeneratorPlan, RGBBlock, image_noise,  # noqa: F401
                       styles_def_to_tensor)
 from .classifiers import MobileNet, ResNet, make_classifier  # noqa: F401
-from .attfind import (attfind_extraction, attfind_select, attfind_sweep, filter_unstable_images,  # noqa: F401
+from .attfind import (attfind_extraction, attfind_select, attfind_sweep, attfind_verify_topk, filter_unstable_images,  # noqa: F401
                       find_significant_styles, get_min_max_style_vectors, load_records, save_records,
                       sindex_to_block_idx_and_index)
 from .counterfactual import (draw_on_image, generate_change_image_given_dlatent, generate_images_given_dlatent,  # noqa: F401

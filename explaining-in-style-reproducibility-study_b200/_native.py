@@ -71,6 +71,7 @@ SIGNATURES = {
                                      c_size_t, c_void_p]),
     "sx_attfind_minmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sx_attfind_make_styles": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "sx_attfind_make_styles_list": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_int, c_float, c_void_p]),
     "sx_attfind_scatter_effects": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "sx_attfind_select_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sx_attfind_select": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
@@ -111,8 +112,8 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.sx_version() != 100:
-            raise RuntimeError(f"{LIB_PATH}: version {l.sx_version()} does not match the Python binding (100); rebuild")
+        if l.sx_version() != 101:
+            raise RuntimeError(f"{LIB_PATH}: version {l.sx_version()} does not match the Python binding (101); rebuild")
         _lib = l
     return _lib
 

@@ -479,6 +479,17 @@ int sx_attfind_make_styles(const float* base_row, const float* minima, const flo
   return SX_OK;
 }
 
+int sx_attfind_make_styles_list(const float* base_row, const float* minima, const float* maxima, float* out, int style_row,
+                                int Sc, const int* columns, int count, float shift_size, sx_stream_t stream) {
+  SX_REQUIRE(base_row && minima && maxima && out, "null argument");
+  SX_REQUIRE(style_row >= 1 && Sc >= 1 && Sc <= style_row && count >= 0, "bad range");
+  if (count == 0) return SX_OK;
+  SX_REQUIRE(columns, "null column list");
+  make_styles_list_kernel<<<count, 256, 0, S(stream)>>>(base_row, minima, maxima, out, style_row, Sc, columns, shift_size);
+  SX_CHECK_LAUNCH();
+  return SX_OK;
+}
+
 int sx_attfind_scatter_effects(const float* logits, const float* base_logits, float* effects, int n, int Sc, int first_sindex,
                                int num_coords, sx_stream_t stream) {
   SX_REQUIRE(logits && base_logits && effects, "null argument");

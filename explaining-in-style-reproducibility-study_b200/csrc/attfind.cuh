@@ -47,6 +47,24 @@ __global__ void __launch_bounds__(256) make_styles_kernel(const float* __restric
   }
 }
 
+// the same for an arbitrary list of flat columns x_j = d_j * S + s_j
+__global__ void __launch_bounds__(256) make_styles_list_kernel(const float* __restrict__ base, const float* __restrict__ mn,
+                                                               const float* __restrict__ mx, float* __restrict__ out, int row,
+                                                               int S, const int* __restrict__ columns, float shift_size) {
+  const int j = blockIdx.x;
+  const int x = columns[j];
+  const int s = x % S, d = x / S;
+  float* o = out + (long long)j * row;
+  for (int i = threadIdx.x; i < row; i += blockDim.x) {
+    float v = base[i];
+    if (i == s) {
+      const float target = d == 0 ? mn[s] : mx[s];
+      v = v + (target - v) * shift_size;  // NB:374-375,381
+    }
+    o[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) scatter_effects_kernel(const float* __restrict__ logits, const float* __restrict__ base,
                                                               float* __restrict__ effects, int n, int S, int first_s,
                                                               int count) {

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SX_VERSION 100
+#define SX_VERSION 101
 
 #define SX_OK 0
 #define SX_EINVAL (-1)       /* bad argument */
@@ -213,6 +213,12 @@ int sx_attfind_minmax(const float* style_coords, int N, int S, int row_stride, f
  * with s_j = first_sindex + j / 2, d_j = j % 2 (0: towards minima, 1: towards maxima), j < 2*num_coords. */
 int sx_attfind_make_styles(const float* base_row, const float* minima, const float* maxima, float* out,
                            int style_row, int first_sindex, int num_coords, float shift_size, sx_stream_t stream);
+
+/* The same shift injection for an ARBITRARY list of (direction, coordinate) pairs of ONE latent (the exact re-evaluation
+ * of the top-k candidates, attfind.attfind_verify_topk): columns[j] = d_j * S + s_j (device int32, the flat column index
+ * of NB:745 / 758); out[j, :] = base_row[:] with coordinate s_j moved towards minima (d_j = 0) or maxima (d_j = 1). */
+int sx_attfind_make_styles_list(const float* base_row, const float* minima, const float* maxima, float* out,
+                                int style_row, int S, const int* columns, int count, float shift_size, sx_stream_t stream);
 
 /* NB:385: effects[n, d_j, s_j, :] = logits[j, :] - base_logits[n, :]  (effects [N,2,S,2], logits [2*num_coords, 2]) */
 int sx_attfind_scatter_effects(const float* logits, const float* base_logits, float* effects, int n, int S,

@@ -7,6 +7,8 @@ the per-class greedy picks + the merged list (NB:731-814), with the margins that
   fp32        parity mode: fp32 FFMA generator kernels + the fp32 eager PyTorch classifier, TF32 off
   bench       throughput mode, exactly what bench.py times: bf16 tcgen05 generator + bf16 fused classifier
               (BN folded, s2d stem, native max-pool, native preprocessing)
+  verify      bench + attfind_verify_topk: the candidates of the bench sweep re-evaluated in the parity mode (must give
+              exactly the fp32 arm's picks at a fraction of its cost); needs the bench arm before it
   bf16g_fp32c bf16 generator + fp32 eager classifier (which half of the bench mode moves the effects?)
   oracle      the oracle's own torch functions (oracle/stylex_oracle.py: literal per-sample-weight grouped convs,
               full forwards, no prefix reuse) executed on the GPU in fp32 with TF32 off, batched over coord_shift
@@ -38,7 +40,7 @@ def main():
     ap.add_argument("--image-size", type=int, default=64)
     ap.add_argument("--latents", type=int, default=256)
     ap.add_argument("--classifier", default="resnet")
-    ap.add_argument("--arms", default="fp32,bench,bf16g_fp32c,oracle")
+    ap.add_argument("--arms", default="fp32,bench,verify,bf16g_fp32c,oracle")
     ap.add_argument("--max-batch", type=int, default=256)
     ap.add_argument("--oracle-batch", type=int, default=128)
     ap.add_argument("--oracle-max-seconds", type=float, default=1200.0)
@@ -97,11 +99,30 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         picks, merged, scores = sx.attfind_select(res["style_change"], res["base_prob"], 5, 0.5)
+        sweeps[name] = res
         results[name] = (res["style_change"].cpu().numpy(), res["base_prob"].cpu().numpy())
         record["arms"][name] = {"generator": precision, "classifier": info, "seconds": dt, "coord_evals_per_s": 2 * S * n / dt,
                                 "picks": {str(k): [list(p) for p in v] for k, v in picks.items()},
                                 "merged": [list(p) for p in merged], "scores": scores}
         print(f"[{name}] {dt:.1f} s, {2 * S * n / dt:.0f} coord-evals/s, picks {picks}", flush=True)
+
+    sweeps = {}
+
+    def run_verify(name):
+        c, info = classifier("fp32")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        picks, merged, scores, vi = sx.attfind_verify_topk(G, c, lat, noise, sweeps["bench"], 5, 0.5, precision="fp32", max_batch=128)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        results[name] = (vi["style_change"].cpu().numpy(), vi["base_prob"].cpu().numpy())
+        record["arms"][name] = {"generator": "bf16 sweep, candidates re-evaluated in fp32", "classifier": info, "seconds": dt,
+                                "picks": {str(k): [list(p) for p in v] for k, v in picks.items()},
+                                "merged": [list(p) for p in merged], "scores": scores,
+                                "verify": {k: v for k, v in vi.items() if k not in ("style_change", "base_prob")},
+                                "exact_fraction": vi["exact_evals"] / (2 * S * n)}
+        print(f"[{name}] +{dt:.1f} s, {vi['candidates']} columns exact ({100 * vi['exact_evals'] / (2 * S * n):.2f} % of the coord-evals), "
+              f"band {vi['band']:.3e}, verified {vi['verified']}, picks {picks}", flush=True)
 
     def run_oracle(name):
         """oracle functions on the GPU: full forwards with a functional coordinate shift, batch = oracle_batch."""
@@ -160,6 +181,8 @@ def main():
             run_ours("bench", "bf16", "bench")
         elif arm == "bf16g_fp32c":
             run_ours("bf16g_fp32c", "bf16", "fp32")
+        elif arm == "verify":
+            run_verify("verify")
         elif arm == "oracle":
             run_oracle("oracle")
         else:
@@ -184,7 +207,7 @@ def main():
                    "base_err": float(np.abs(b - b_ref).max()), "picks_equal": None}
         record["margins"][name] = rep
         print(f"[{name} vs {ref_name}] picks_equal={rep.get('picks_equal')} max|eff err|={rep.get('max_abs_effect_err'):.3e} "
-              f"min gap={rep.get('min_gap')} worst 2err/gap={rep.get('worst_2err_over_gap')}", flush=True)
+              f"base err={rep.get('base_err')} min gap={rep.get('min_gap')} worst 2err/gap={rep.get('worst_2err_over_gap')}", flush=True)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         json.dump(record, open(args.out, "w"), indent=1)

@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/stylex_b200.h but not exported"
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
-    assert lib.sx_version() == 100
+    assert lib.sx_version() == 101
     assert lib.sx_generator_workspace_bytes(None, 1, 0) == 0
 
 
@@ -512,3 +512,34 @@ def test_reference_arm_runs_the_staged_reference(tmp_path):
     env = dict(os.environ, STYLEX_REFERENCE_ROOT=staged)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "OK (2, 2, 136, 2)" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("seed,noise", [(0, 1e-2), (1, 3e-2), (2, 1e-3), (3, 1e-1)])
+def test_screen_and_verify_recovers_the_exact_topk(seed, noise):
+    """attfind.screen_and_verify (the host logic of attfind_verify_topk): from NOISY effects (a bf16 sweep) and an oracle
+    for exact columns it returns exactly the picks / merged list of the selection on the exact effects, re-evaluating a
+    small fraction of the columns.  Near-flat column means (the hard case: leaders closer than the noise)."""
+    from oracle import stylex_oracle as O
+    rng = np.random.default_rng(seed)
+    n, S = 48, 400
+    exact = (rng.normal(size=(n, 2, S, 2)) * 0.4 + 0.05 * rng.normal(size=(1, 2, S, 2))).astype(np.float32)
+    base = rng.normal(size=(n, 2)).astype(np.float32)
+    approx = exact + (rng.normal(size=exact.shape) * noise * (0.2 + np.abs(exact))).astype(np.float32)
+    want = O.attfind_select(exact, base, 5, 0.5)
+    calls = []
+
+    def exact_columns(cols):
+        calls.append(len(cols))
+        return torch.from_numpy(exact).reshape(n, 2 * S, 2)[:, torch.tensor(cols)]
+
+    def select(eff, b, k, thr):
+        return O.attfind_select(eff.numpy(), b.numpy(), k, thr)
+
+    picks, merged, scores, info = attfind.screen_and_verify(torch.from_numpy(approx), torch.from_numpy(base), exact_columns,
+                                                            select, 5, 0.5, min_candidates=16)
+    assert info["verified"], info
+    assert picks == want[0] and merged == want[1]
+    assert scores == want[2]
+    assert sum(calls) <= 2 * S and info["candidates"] == sum(calls)
+    if noise <= 1e-2:
+        assert sum(calls) < 0.5 * 2 * S                                            # a fraction of the 2S columns
