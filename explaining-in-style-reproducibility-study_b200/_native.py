@@ -49,6 +49,7 @@ SIGNATURES = {
     "sx_blur3x3_reflect": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sx_noise_lrelu": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "sx_rgb_add_upsample_blur": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
+    "sx_rgb_prefill_upsample_blur": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sx_linear_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "sx_linear_bwd": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
     "sx_noise_lrelu_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -71,7 +72,8 @@ SIGNATURES = {
                                      c_size_t, c_void_p]),
     "sx_attfind_minmax": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sx_attfind_make_styles": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
-    "sx_attfind_make_styles_list": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_int, c_float, c_void_p]),
+    "sx_attfind_make_styles_pairs": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                             c_int, c_float, c_void_p]),
     "sx_attfind_scatter_effects": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "sx_attfind_select_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sx_attfind_select": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,

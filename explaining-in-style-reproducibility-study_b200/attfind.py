@@ -256,56 +256,50 @@ def attfind_select(style_change_effect: torch.Tensor, base_probs: torch.Tensor, 
 # ---------------------------------------------------------------------------------------------
 # exact top-k from a throughput-mode sweep: screen in bf16, verify the candidates in fp32
 # ---------------------------------------------------------------------------------------------
-def _conv_of_coord(conv_coords, s: int) -> int:
-    for conv, (off, width) in enumerate(conv_coords):
-        if off <= s < off + width:
-            return conv
-    raise IndexError(s)
-
-
 @torch.no_grad()
-def _exact_columns(G: Generator, classifier, lat: torch.Tensor, noise: torch.Tensor, styles_all: torch.Tensor,
-                   base_exact: torch.Tensor, minima: torch.Tensor, maxima: torch.Tensor, columns: Sequence[int], lo: int, hi: int,
+def _exact_entries(G: Generator, classifier, noise: torch.Tensor, styles_all: torch.Tensor, base_exact: torch.Tensor,
+                   minima: torch.Tensor, maxima: torch.Tensor, latent_idx: torch.Tensor, columns: torch.Tensor,
                    shift_size: float, precision: str, max_batch: int) -> torch.Tensor:
-    """Parity-mode effects of the flat columns ``x = d*S + s`` for the latents [lo, hi): [hi-lo, len(columns), 2]."""
+    """Parity-mode effects of the (latent n_j, flat column x_j = d*S + s) pairs: [len, 2].
+
+    Full generator forwards (start_conv = 0 needs no per-latent prefix cache), so one batch mixes latents freely:
+    ``sx_attfind_make_styles_pairs`` writes row j = style row of latent n_j with coordinate s_j moved to its minimum /
+    maximum (NB:374-381 as data), then generator + classifier + logit delta (NB:382-385)."""
     plan = G.plan()
     lib = N.lib()
     S, row = plan.S, plan.row
-    dev = lat.device
-    cols = sorted(int(x) for x in columns)
-    order = sorted(range(len(cols)), key=lambda j: (cols[j] % S, cols[j] // S))      # by coordinate => by conv
-    cols_sorted = [cols[j] for j in order]
-    out = torch.zeros(hi - lo, len(cols), 2, device=dev, dtype=torch.float32)
-    if not cols or hi <= lo:
+    dev = styles_all.device
+    n = int(latent_idx.numel())
+    out = torch.empty(n, 2, device=dev, dtype=torch.float32)
+    if n == 0:
         return out
-    col_dev = torch.tensor(cols_sorted, device=dev, dtype=torch.int32)
-    pos = torch.tensor(order, device=dev, dtype=torch.long)
+    li = latent_idx.to(device=dev, dtype=torch.int32).contiguous()
+    ci = columns.to(device=dev, dtype=torch.int32).contiguous()
     plan.reserve(max_batch, precision)
     stream = N.stream_ptr()
     styles_b = torch.empty(max_batch, row, device=dev, dtype=torch.float32)
-    for n in range(lo, hi):
-        plan.forward(styles_all[n: n + 1], noise, save_cache=True, precision=precision)
-        for j0 in range(0, len(cols_sorted), max_batch):
-            cnt = min(max_batch, len(cols_sorted) - j0)
-            start = _conv_of_coord(plan.conv_coords, cols_sorted[j0] % S)        # earliest conv touched by this chunk
-            N.check(lib.sx_attfind_make_styles_list(styles_all[n].data_ptr(), minima.data_ptr(), maxima.data_ptr(),
-                                                    styles_b.data_ptr(), row, S, col_dev[j0:].data_ptr(), cnt, float(shift_size),
-                                                    stream), "sx_attfind_make_styles_list")
-            rgb = plan.forward(styles_b[:cnt], noise, start_conv=start, precision=precision)
-            logits = classifier.classify_images(rgb).float()
-            out[n - lo, pos[j0: j0 + cnt]] = logits - base_exact[n]
+    for j0 in range(0, n, max_batch):
+        cnt = min(max_batch, n - j0)
+        N.check(lib.sx_attfind_make_styles_pairs(styles_all.data_ptr(), styles_all.stride(0), minima.data_ptr(), maxima.data_ptr(),
+                                                 styles_b.data_ptr(), row, S, li[j0:].data_ptr(), ci[j0:].data_ptr(), cnt,
+                                                 float(shift_size), stream), "sx_attfind_make_styles_pairs")
+        rgb = plan.forward(styles_b[:cnt], noise, precision=precision)
+        logits = classifier.classify_images(rgb).float()
+        out[j0: j0 + cnt] = logits - base_exact[li[j0: j0 + cnt].long()]
     return out
 
 
-def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_columns, select, num_indices: int = 5,
+def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_entries, select, num_indices: int = 5,
                       effect_threshold: float = 0.5, min_candidates: int = 32, band_sigmas: float = 8.0,
                       band_floor: float = 2.0, max_passes: int = 6):
     """The selection logic of ``attfind_verify_topk`` (device-agnostic torch; see there).
 
     approx [N,2,S,2]: effects of the throughput-mode sweep; base_exact [N,2]: parity-mode base logits;
-    ``exact_columns(list of flat columns x = d*S + s) -> [N, len, 2]``: parity-mode effects of those columns for ALL
-    latents; ``select(effects, base_logits, k, effect_threshold) -> (picks, merged, scores)``: the exact selection
-    (``attfind_select``).  Returns (picks, merged, scores, info)."""
+    ``exact_entries(latent_idx [P], columns [P]) -> [P, 2]``: parity-mode effects of the (latent, flat column x = d*S + s)
+    pairs; ``select(effects, base_logits, k, effect_threshold) -> (picks, merged, scores)``: the exact selection
+    (``attfind_select``).  Candidate columns of class c are re-evaluated for the images of class c only (the greedy
+    selection of class c reads nothing else); the picked columns and their opposite directions, which the merged ranking
+    reads over ALL images (NB:806-809), are completed at the end.  Returns (picks, merged, scores, info)."""
     n_all, _, S, _ = approx.shape
     dev = approx.device
     k = int(num_indices)
@@ -315,29 +309,43 @@ def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_colu
         if int((labels == c).sum()) == 0:
             raise IndexError(f"AttFind selection: class {c} has no images (the notebook fails here too, quirk Q7)")
     hybrid = approx.float().clone()
-    is_exact = torch.zeros(2 * S, dtype=torch.bool, device=dev)
+    flat = hybrid.view(n_all, 2 * S, 2)
     rows = {c: (labels == c).nonzero().flatten() for c in (0, 1)}
+    is_exact = {c: torch.zeros(2 * S, dtype=torch.bool, device=dev) for c in (0, 1)}
     E_apx = {c: approx[rows[c]][:, :, :, c].reshape(rows[c].numel(), 2 * S).double().clamp_(min=0) for c in (0, 1)}
-    info = {"passes": 0, "exact_evals": 0, "band": None, "candidates": 0, "verified": False}
+    info = {"passes": 0, "exact_evals": 0, "band": None, "candidates": [0, 0], "verified": False}
     neg_inf = torch.full((2 * S,), float("-inf"), device=dev, dtype=torch.float64)
 
-    def make_exact(columns):
-        columns = sorted(set(int(x) for x in columns) - set(is_exact.nonzero().flatten().tolist()))
-        if not columns:
+    def make_exact(per_class_columns):
+        """{class: columns}: one call of ``exact_entries`` for the (row of class c, new column of class c) pairs"""
+        li, ci, todo = [], [], {}
+        for c, columns in per_class_columns.items():
+            cols = sorted(set(int(x) for x in columns) - set(is_exact[c].nonzero().flatten().tolist()))
+            if not cols:
+                continue
+            cols_t = torch.tensor(cols, device=dev, dtype=torch.long)
+            todo[c] = cols_t
+            li.append(rows[c].repeat_interleave(len(cols)))
+            ci.append(cols_t.repeat(rows[c].numel()))
+        if not todo:
             return
-        full = exact_columns(columns)                                              # [N, len(columns), 2]
-        idx = torch.tensor(columns, device=dev, dtype=torch.long)
-        hybrid.view(n_all, 2 * S, 2)[:, idx] = full.to(hybrid.dtype)
-        is_exact[idx] = True
-        info["exact_evals"] += len(columns) * n_all
-        info["candidates"] = int(is_exact.sum())
+        vals = exact_entries(torch.cat(li), torch.cat(ci))                         # [P, 2]
+        off = 0
+        for c, cols_t in todo.items():
+            cnt = rows[c].numel() * cols_t.numel()
+            flat[rows[c][:, None], cols_t[None, :]] = vals[off: off + cnt].reshape(rows[c].numel(), cols_t.numel(), 2).to(flat.dtype)
+            off += cnt
+            is_exact[c][cols_t] = True
+        info["exact_evals"] += int(vals.shape[0])
+        info["candidates"] = [int(is_exact[0].sum()), int(is_exact[1].sum())]
 
     def replay(band=None, collect_top=0):
         """the greedy selection (NB:751-756) on the hybrid effects, winners restricted to exact columns.
-        -> (every round verified, columns to add, flat picks per class, approx-minus-exact column-mean discrepancies)"""
-        ok, need, picks, disc = True, set(), {}, []
-        have_exact = bool(is_exact.any())
+        -> (every round verified, {class: columns to add}, flat picks per class, approx-minus-exact column-mean discrepancies)"""
+        ok, need, picks, disc = True, {0: set(), 1: set()}, {}, []
         for c in (0, 1):
+            ex = is_exact[c]
+            have_exact = bool(ex.any())
             E = hybrid[rows[c]][:, :, :, c].reshape(rows[c].numel(), 2 * S).double().clamp_(min=0)
             Ea = E_apx[c].clone()
             img = torch.zeros(E.shape[0], device=dev, dtype=torch.float64)
@@ -349,15 +357,15 @@ def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_colu
                     continue
                 cm = E[mask].mean(dim=0)
                 if collect_top:
-                    need.update(torch.topk(cm, min(collect_top, cm.numel())).indices.tolist())
-                x = int(torch.argmax(torch.where(is_exact, cm, neg_inf))) if have_exact else int(torch.argmax(cm))
+                    need[c].update(torch.topk(cm, min(collect_top, cm.numel())).indices.tolist())
+                x = int(torch.argmax(torch.where(ex, cm, neg_inf))) if have_exact else int(torch.argmax(cm))
                 if have_exact:
-                    disc.append((Ea[mask].mean(dim=0) - cm)[is_exact])
+                    disc.append((Ea[mask].mean(dim=0) - cm)[ex])
                 if band is not None:
-                    viol = ((~is_exact) & (cm + band >= cm[x])).nonzero().flatten()
+                    viol = ((~ex) & (cm + band >= cm[x])).nonzero().flatten()
                     if viol.numel():
                         ok = False
-                        need.update(viol.tolist())
+                        need[c].update(viol.tolist())
                 picks[c].append(x)
                 img += E[:, x]
                 E[:, x] = 0
@@ -379,9 +387,12 @@ def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_colu
         if ok:
             info["verified"] = True
             break
+        # add the violators plus everything within a further band of them, so that a second pass is rarely needed
         make_exact(need)
-    # the merged ranking (NB:806-809) reads both directions of every picked coordinate over all images
-    make_exact([(1 - x // S) * S + x % S for c in (0, 1) for x in picks_r[c]])
+    # the merged ranking (NB:806-809) reads both directions of every picked coordinate over ALL images
+    both = [x for c in (0, 1) for x in picks_r[c]]
+    both += [(1 - x // S) * S + x % S for x in both]
+    make_exact({0: both, 1: both})
     picks, merged, scores = select(hybrid, base_exact, k, effect_threshold)
     want = {c: [(x // S, x % S) for x in picks_r[c]] for c in (0, 1)}
     if picks != want:                 # can only happen on an exact float64 tie between two exact columns
@@ -408,15 +419,17 @@ def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: 
        "fp32"), each latent by the rank that owns it: the class split (NB:695-714) is exact;
     2. replays the greedy selection on the approximate effects ``sweep['style_change']`` and takes, per class and round,
        the ``min_candidates`` leading columns as candidates;
-    3. re-evaluates the candidate columns for every latent in the parity mode (``sx_attfind_make_styles_list`` + suffix
-       forwards, latents sharded over ranks like the sweep, one small all-gather) and overwrites them in the effects;
+    3. re-evaluates (image of class c, candidate column of class c) in the parity mode -- full forwards batched across
+       latents (``sx_attfind_make_styles_pairs``), the pair list split evenly over the ranks, one small all-gather -- and
+       overwrites those entries of the effects;
     4. measures the approximate-vs-exact discrepancy d of the candidates' masked column means and sets
        ``band = max(band_sigmas * std(d), band_floor * max|d|)``;
     5. replays the selection on the hybrid effects: a round is VERIFIED when its winner is an exact column and no
        non-candidate column comes within ``band`` of it (its true mean then cannot exceed the winner's).  Columns that do
        are added to the candidates and steps 3-5 repeat (``max_passes``);
-    6. the opposite-direction columns of the picks (needed by the merged ranking, NB:806-809) are made exact too, and the
-       final picks / merged list come from ``attfind_select`` (numpy-exact float64 kernels) on the hybrid effects.
+    6. the picked columns and their opposite directions (the merged ranking reads them over ALL images, NB:806-809) are
+       completed, and the final picks / merged list come from ``attfind_select`` (numpy-exact float64 kernels) on the
+       hybrid effects.
 
     The picks equal those of a full parity-mode sweep whenever the band holds for the columns that were NOT re-evaluated
     (8 sigma of the measured error by default).  Returns (picks, merged, scores, info): ``info['verified']`` says whether
@@ -425,33 +438,38 @@ def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: 
     plan = G.plan()
     S, L = plan.S, G.num_layers
     n_all = latents.shape[0]
+    dev = latents.device
     lat = N.f32c(latents)
     minima, maxima = N.f32c(sweep["minima"]).reshape(-1), N.f32c(sweep["maxima"]).reshape(-1)
-    lo, hi = shard_range(n_all, rank, world_size)
     styles_all = plan.styles(styles_def_to_tensor([(lat, L)]).contiguous())
     approx = sweep["style_change"]
     if tuple(approx.shape) != (n_all, 2, S, 2):
         raise ValueError(f"sweep['style_change'] must be the gathered [N,2,S,2] tensor, got {tuple(approx.shape)}")
 
-    def gather(t):                                                                 # [hi-lo, ...] -> [N, ...]
+    def gather_rows(t, total):                                                     # contiguous shares [cnt_r, 2] -> [total, 2]
         if world_size == 1:
             return t
         from .dist import gather_effects
-        return gather_effects(t.contiguous(), n_all, world_size)
+        return gather_effects(t.contiguous(), total, world_size)
 
+    # exact base logits: latent n by rank owner(n), gathered (bit-identical everywhere)
+    lo, hi = shard_range(n_all, rank, world_size)
     plan.reserve(max_batch, precision)
-    base_loc = torch.empty(hi - lo, 2, device=lat.device, dtype=torch.float32)
+    base_loc = torch.empty(hi - lo, 2, device=dev, dtype=torch.float32)
     for i in range(lo, hi, max_batch):
         j = min(hi, i + max_batch)
         rgb = plan.forward(styles_all[i:j].contiguous(), noise, precision=precision)
         base_loc[i - lo: j - lo] = classifier.classify_images(rgb).float()
-    base_exact = gather(base_loc)
+    base_exact = gather_rows(base_loc, n_all)
 
-    def exact_columns(columns):
-        return gather(_exact_columns(G, classifier, lat, noise, styles_all, base_exact, minima, maxima, columns, lo, hi,
-                                     shift_size, precision, max_batch))
+    def exact_entries(latent_idx, columns):
+        total = int(latent_idx.numel())
+        plo, phi = shard_range(total, rank, world_size)                            # this rank's share of the pair list
+        loc = _exact_entries(G, classifier, noise, styles_all, base_exact, minima, maxima, latent_idx[plo:phi], columns[plo:phi],
+                             shift_size, precision, max_batch)
+        return gather_rows(loc, total)
 
-    return screen_and_verify(approx, base_exact, exact_columns, attfind_select, num_indices, effect_threshold,
+    return screen_and_verify(approx, base_exact, exact_entries, attfind_select, num_indices, effect_threshold,
                              min_candidates, band_sigmas, band_floor, max_passes)
 
 

@@ -318,6 +318,13 @@ int sx_rgb_add_upsample_blur(const float* rgb, const float* prev, float* out, in
   return SX_OK;
 }
 
+int sx_rgb_prefill_upsample_blur(const float* prev, int prev_batch, float* out, int B, int h, int w, sx_stream_t stream) {
+  SX_REQUIRE(prev && out, "null argument");
+  SX_REQUIRE(B >= 0 && h >= 2 && w >= 2, "bad shape");
+  SX_REQUIRE(prev_batch == 1 || prev_batch == B, "prev batch %d must be 1 or B=%d", prev_batch, B);
+  return launch_rgb_prev_up_blur(prev, prev_batch == 1 ? 0 : (long long)3 * h * w, out, B, 2 * h, 2 * w, S(stream));
+}
+
 int sx_linear_fwd(const float* x, const float* weight, const float* bias, float* out, int B, int in_f, int out_f,
                   sx_stream_t stream) {
   SX_REQUIRE(x && weight && out, "null argument");
@@ -479,13 +486,15 @@ int sx_attfind_make_styles(const float* base_row, const float* minima, const flo
   return SX_OK;
 }
 
-int sx_attfind_make_styles_list(const float* base_row, const float* minima, const float* maxima, float* out, int style_row,
-                                int Sc, const int* columns, int count, float shift_size, sx_stream_t stream) {
-  SX_REQUIRE(base_row && minima && maxima && out, "null argument");
-  SX_REQUIRE(style_row >= 1 && Sc >= 1 && Sc <= style_row && count >= 0, "bad range");
+int sx_attfind_make_styles_pairs(const float* styles_all, long long row_stride, const float* minima, const float* maxima, float* out,
+                                 int style_row, int Sc, const int* latent_idx, const int* columns, int count, float shift_size,
+                                 sx_stream_t stream) {
+  SX_REQUIRE(styles_all && minima && maxima && out, "null argument");
+  SX_REQUIRE(style_row >= 1 && Sc >= 1 && Sc <= style_row && row_stride >= style_row && count >= 0, "bad range");
   if (count == 0) return SX_OK;
-  SX_REQUIRE(columns, "null column list");
-  make_styles_list_kernel<<<count, 256, 0, S(stream)>>>(base_row, minima, maxima, out, style_row, Sc, columns, shift_size);
+  SX_REQUIRE(latent_idx && columns, "null index list");
+  make_styles_pairs_kernel<<<count, 256, 0, S(stream)>>>(styles_all, row_stride, minima, maxima, out, style_row, Sc, latent_idx,
+                                                         columns, shift_size);
   SX_CHECK_LAUNCH();
   return SX_OK;
 }

@@ -47,13 +47,16 @@ __global__ void __launch_bounds__(256) make_styles_kernel(const float* __restric
   }
 }
 
-// the same for an arbitrary list of flat columns x_j = d_j * S + s_j
-__global__ void __launch_bounds__(256) make_styles_list_kernel(const float* __restrict__ base, const float* __restrict__ mn,
-                                                               const float* __restrict__ mx, float* __restrict__ out, int row,
-                                                               int S, const int* __restrict__ columns, float shift_size) {
+// the same for arbitrary (latent n_j, flat column x_j = d_j * S + s_j) pairs: row j starts as the style row of latent n_j
+__global__ void __launch_bounds__(256) make_styles_pairs_kernel(const float* __restrict__ styles_all, long long row_stride,
+                                                                const float* __restrict__ mn, const float* __restrict__ mx,
+                                                                float* __restrict__ out, int row, int S,
+                                                                const int* __restrict__ latent_idx, const int* __restrict__ columns,
+                                                                float shift_size) {
   const int j = blockIdx.x;
   const int x = columns[j];
   const int s = x % S, d = x / S;
+  const float* base = styles_all + (long long)latent_idx[j] * row_stride;
   float* o = out + (long long)j * row;
   for (int i = threadIdx.x; i < row; i += blockDim.x) {
     float v = base[i];

@@ -407,9 +407,82 @@ __global__ void __launch_bounds__(128) rgb_prev_up_blur_kernel(const float* __re
   }
 }
 
+// The same arithmetic (horizontal 3-tap per low-res row, then vertical 3-tap, identical operation order) with one
+// thread = a 2x2 block of low-res pixels = a 4x4 block of outputs per channel: 48 loads serve 48 outputs (the quad form:
+// 27 for 12) and every output row leaves as one 16-byte store (a warp writes 512 contiguous bytes per row).
+__global__ void __launch_bounds__(128) rgb_prev_up_blur4_kernel(const float* __restrict__ prev, long long prev_bstride,
+                                                                float* __restrict__ rgb, int h, int w) {
+  const int H = 2 * h, W = 2 * w;
+  const int b = blockIdx.z;
+  const int i0 = 2 * blockIdx.y;
+  const int jp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * jp >= w) return;
+  const int j0 = 2 * jp;
+  const float* pp = prev + (long long)b * prev_bstride;
+  float* dst = rgb + (long long)b * 3 * H * W;
+  // weights of output row 2*i0 + r over the low-res rows (i-1, i, i+1), i = i0 + (r >> 1); likewise for columns
+  float cy[4][3], cx[4][3];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const bool odd = r & 1;
+    cy[r][0] = cx[r][0] = odd ? 0.0625f : 0.3125f;
+    cy[r][1] = cx[r][1] = 0.625f;
+    cy[r][2] = cx[r][2] = odd ? 0.3125f : 0.0625f;
+  }
+  if (i0 < 1 || i0 + 1 > h - 2) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) blur_up_weights(2 * i0 + r, h, cy[r]);
+  }
+  if (j0 < 1 || j0 + 1 > w - 2) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) blur_up_weights(2 * j0 + r, w, cx[r]);
+  }
+  int rr[4], cc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    rr[k] = min(max(i0 - 1 + k, 0), h - 1);
+    cc[k] = min(max(j0 - 1 + k, 0), w - 1);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* p = pp + (size_t)c * h * w;
+    float hx[4][4];   // [low-res row k][output column q]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* q = p + (size_t)rr[k] * w;
+      const float v0 = __ldg(q + cc[0]), v1 = __ldg(q + cc[1]), v2 = __ldg(q + cc[2]), v3 = __ldg(q + cc[3]);
+      hx[k][0] = cx[0][0] * v0 + cx[0][1] * v1 + cx[0][2] * v2;
+      hx[k][1] = cx[1][0] * v0 + cx[1][1] * v1 + cx[1][2] * v2;
+      hx[k][2] = cx[2][0] * v1 + cx[2][1] * v2 + cx[2][2] * v3;
+      hx[k][3] = cx[3][0] * v1 + cx[3][1] * v2 + cx[3][2] * v3;
+    }
+    float* d = dst + ((size_t)c * H + 2 * i0) * W + 2 * j0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int k0 = r >> 1;   // output rows 0,1 read low-res rows k = 0..2; rows 2,3 read k = 1..3
+      float4 o;
+      o.x = cy[r][0] * hx[k0][0] + cy[r][1] * hx[k0 + 1][0] + cy[r][2] * hx[k0 + 2][0];
+      o.y = cy[r][0] * hx[k0][1] + cy[r][1] * hx[k0 + 1][1] + cy[r][2] * hx[k0 + 2][1];
+      o.z = cy[r][0] * hx[k0][2] + cy[r][1] * hx[k0 + 1][2] + cy[r][2] * hx[k0 + 2][2];
+      o.w = cy[r][0] * hx[k0][3] + cy[r][1] * hx[k0 + 1][3] + cy[r][2] * hx[k0 + 2][3];
+      *reinterpret_cast<float4*>(d + (size_t)r * W) = o;
+    }
+  }
+}
+
 inline int launch_rgb_prev_up_blur(const float* prev, long long prev_bstride, float* rgb, int B, int H, int W, cudaStream_t st) {
   if (B == 0) return SX_OK;
   SX_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 4 && W >= 4, "rgb_prev: bad size %dx%d", H, W);
+  static const bool quad_only = getenv("SX_RGB_PREV_QUAD") != nullptr;   // A/B: the one-quad-per-thread form
+  if (!quad_only && H % 4 == 0 && W % 4 == 0 && H >= 16 && W >= 16 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0) {
+    const int wp = W / 4;                                   // low-res column pairs
+    const int threads = wp >= 128 ? 128 : (wp >= 64 ? 64 : 32);
+    dim3 grid((wp + threads - 1) / threads, H / 4, B);
+    SX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "rgb_prev: grid too large");
+    rgb_prev_up_blur4_kernel<<<grid, threads, 0, st>>>(prev, prev_bstride, rgb, H / 2, W / 2);
+    SX_CHECK_LAUNCH();
+    return SX_OK;
+  }
   const int w = W / 2;
   const int threads = w >= 128 ? 128 : (w >= 64 ? 64 : 32);
   dim3 grid((w + threads - 1) / threads, H / 2, B);

@@ -890,7 +890,9 @@ inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int 
 
 // SX_HALO_VARIANT (bitmask, tuning experiments): 1 = the 32 -> 32 layers run 2 epilogue sets (wide passes) instead of 4;
 // 2 = the 64 -> 64 layers run 2 sets x 2 tiles with two MMA warps instead of 4 sets x 1 tile with one;
-// 4 = the fused-upsample 128 -> 64 layer runs 2 tiles per slot with two MMA warps
+// 4 = the fused-upsample 128 -> 64 layer runs 2 tiles per slot with two MMA warps;
+// 8 = the weight-streaming Co = 128 layers run an 8-deep weight ring (3 activation stages); 16 = 10-deep (2 activation stages)
+// SX_HALO_MAX_CO: plain (non-upsample) layers wider than this go to conv_tc_kernel instead (A/B of the two kernels)
 inline int halo_variant() {
   static const int v = getenv("SX_HALO_VARIANT") ? atoi(getenv("SX_HALO_VARIANT")) : 0;
   return v;
@@ -901,6 +903,8 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
                             const ConvEpilogue& ep, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (!halo_shape_supported(Ci, Co, H, W) || B == 0) return SX_OK;
+  static const int max_co = getenv("SX_HALO_MAX_CO") ? atoi(getenv("SX_HALO_MAX_CO")) : 128;
+  if (Co > max_co) return SX_OK;
   const int bk = Ci % 64 == 0 ? 64 : 32;
   const ConvHaloParams p = make_halo_params(B, Ci, Co, H, W, bk, ep);
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
@@ -919,7 +923,11 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   // 128 -> 64 channels (147 KB of weights): still resident, with a 2-deep activation ring
   if (Co == 64 && bk == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg<64, 64, 2, 2, true, 4, 1, 1>(x, wk, p, stream);
   if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 3, 6, false, 4, 1, 1>(x, wk, p, stream);
-  if (Co == 128 && bk == 64) return launch_conv_halo_cfg<128, 64, 3, 4, false, 2, 2, 1>(x, wk, p, stream);
+  if (Co == 128 && bk == 64) {
+    if (halo_variant() & 8) return launch_conv_halo_cfg<128, 64, 3, 8, false, 2, 2, 1>(x, wk, p, stream);
+    if (halo_variant() & 16) return launch_conv_halo_cfg<128, 64, 2, 10, false, 2, 2, 1>(x, wk, p, stream);
+    return launch_conv_halo_cfg<128, 64, 3, 4, false, 2, 2, 1>(x, wk, p, stream);
+  }
   *handled = false;
   return SX_OK;
 }
@@ -946,6 +954,8 @@ inline int launch_conv_halo_ups(const __nv_bfloat16* xlow, const __nv_bfloat16* 
     return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 4, 8, 1, 1>(xlow, wk, p, stream);
   }
   if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true, 4, 8, 1, 1>(xlow, wk, p, stream);
+  if (halo_variant() & 8) return launch_conv_halo_cfg2<128, 64, 3, 8, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  if (halo_variant() & 16) return launch_conv_halo_cfg2<128, 64, 2, 10, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
   return launch_conv_halo_cfg2<128, 64, 3, 4, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
 }
 

@@ -99,6 +99,11 @@ int sx_noise_lrelu(const float* x, const float* inoise, const float* noise_w, co
 int sx_rgb_add_upsample_blur(const float* rgb, const float* prev, float* out, int B, int C, int H, int W,
                              int upsample, sx_stream_t stream);
 
+/* RGBBlock.upsample alone -- ST:613-616,626-627: out[b] = blur(upsample2x(prev[b | 0])) for 3-channel planes, the pre-fill
+ * of the rgb plane a fused-ToRGB conv2 epilogue accumulates into (generator plan).  prev [prev_batch,3,h,w] with
+ * prev_batch 1 (one cached plane broadcast to the batch, AttFind suffix forwards) or B; out [B,3,2h,2w]. */
+int sx_rgb_prefill_upsample_blur(const float* prev, int prev_batch, float* out, int B, int h, int w, sx_stream_t stream);
+
 /* nn.Linear -- to_style1/2, RGBBlock.to_style (ST:608,681,685).  x[B,in], weight[out,in], bias[out] -> out[B,out] */
 int sx_linear_fwd(const float* x, const float* weight, const float* bias, float* out, int B, int in_features,
                   int out_features, sx_stream_t stream);
@@ -214,11 +219,14 @@ int sx_attfind_minmax(const float* style_coords, int N, int S, int row_stride, f
 int sx_attfind_make_styles(const float* base_row, const float* minima, const float* maxima, float* out,
                            int style_row, int first_sindex, int num_coords, float shift_size, sx_stream_t stream);
 
-/* The same shift injection for an ARBITRARY list of (direction, coordinate) pairs of ONE latent (the exact re-evaluation
- * of the top-k candidates, attfind.attfind_verify_topk): columns[j] = d_j * S + s_j (device int32, the flat column index
- * of NB:745 / 758); out[j, :] = base_row[:] with coordinate s_j moved towards minima (d_j = 0) or maxima (d_j = 1). */
-int sx_attfind_make_styles_list(const float* base_row, const float* minima, const float* maxima, float* out,
-                                int style_row, int S, const int* columns, int count, float shift_size, sx_stream_t stream);
+/* The same shift injection for ARBITRARY (latent, direction, coordinate) triples -- the exact re-evaluation of the top-k
+ * candidates (attfind.attfind_verify_topk), batched across latents: styles_all [N, row_stride] are the style rows of all
+ * latents, latent_idx[j] / columns[j] (device int32) name the latent and the flat column d_j * S + s_j (the index of
+ * NB:745 / 758); out[j, :] = styles_all[latent_idx[j], :style_row] with coordinate s_j moved towards minima (d_j = 0) or
+ * maxima (d_j = 1) by shift_size (NB:374-381). */
+int sx_attfind_make_styles_pairs(const float* styles_all, long long row_stride, const float* minima, const float* maxima,
+                                 float* out, int style_row, int S, const int* latent_idx, const int* columns, int count,
+                                 float shift_size, sx_stream_t stream);
 
 /* NB:385: effects[n, d_j, s_j, :] = logits[j, :] - base_logits[n, :]  (effects [N,2,S,2], logits [2*num_coords, 2]) */
 int sx_attfind_scatter_effects(const float* logits, const float* base_logits, float* effects, int n, int S,

@@ -309,9 +309,11 @@ def test_attfind_sweep_64px_subset_vs_oracle(dev, kind):
 
 
 def test_attfind_bf16_sweep_close_to_fp32(dev, tc_ok):
-    """bf16 generator vs fp32 generator under the same fp32 classifier, coordinates spread over every conv.  Bounds from
-    the measured config-2 job (profiles/r02_topk_parity_64.json: max 1.8 %, rms 0.25 % of the largest effect), with 2x
-    head-room -- NOT a statement about picks; the picks are covered by test_topk_* below."""
+    """bf16 generator vs fp32 generator under the same fp32 classifier, coordinates spread over every conv.  The bf16
+    perturbation of an effect is ABSOLUTE (rounding noise of the activations seen through the classifier), not relative to
+    the effect: measured max 5.6e-2 / rms 1.3e-2 here and max 7.3e-2 / rms 1.0e-2 on the 256-latent config-2 job
+    (profiles/r02_topk_parity_64.json).  Bounds = those with 2x head-room.  NOT a statement about picks -- the picks
+    are covered by test_topk_* below, whose verification pass is what makes them exact."""
     _need_tc(tc_ok)
     sd, G, lat, noise, clf_cpu, clf_gpu = _config64(dev, "resnet", 3)
     S = G.num_style_coords
@@ -323,8 +325,8 @@ def test_attfind_bf16_sweep_close_to_fp32(dev, tc_ok):
     mag = r32["style_change"].abs().max().item()
     print(f"bf16 vs fp32 effects: max err {err:.3e}, rms {rms:.3e}, max|effect| {mag:.3e}")
     assert mag > 1e-2
-    assert err <= 0.04 * mag + 1e-2
-    assert rms <= 0.006 * mag + 2e-3
+    assert err <= 0.15
+    assert rms <= 0.03
 
 
 def _bench_mode_classifier(dev, model, G, noise, size=64):
@@ -1031,3 +1033,18 @@ def test_generator_backward_bf16(dev, tc_ok):
         assert _rel(params[n].grad, ref[n]) <= 1e-1, n
         assert cos(params[n].grad, ref[n]) >= 0.99, n
     assert _rel(st.grad, ref_st) <= 1e-1 and cos(st.grad, ref_st) >= 0.99
+
+
+@pytest.mark.parametrize("h,batch,bcast", [(2, 3, False), (4, 2, True), (8, 5, False), (16, 3, True), (64, 2, False), (128, 2, True)])
+def test_rgb_prefill_upsample_blur_vs_oracle(dev, h, batch, bcast):
+    """RGBBlock.upsample = Sequential(Upsample(bilinear x2), Blur) ST:613-616 as the closed-form pre-fill kernels of the
+    fused ToRGB (one 2x2 quad per thread for small planes, one 4x4 block per thread from 16 px up; borders included),
+    with and without the batch broadcast of the AttFind suffix forwards."""
+    torch.manual_seed(h)
+    prev = torch.randn(1 if bcast else batch, 3, h, h)
+    ref = O.blur3x3_reflect(O.upsample2x(prev)).expand(batch, -1, -1, -1)
+    out = torch.full((batch, 3, 2 * h, 2 * h), float("nan"), device=dev)
+    pd = prev.to(dev).contiguous()
+    _native.check(_native.lib().sx_rgb_prefill_upsample_blur(pd.data_ptr(), pd.shape[0], out.data_ptr(), batch, h, h,
+                                                             _native.stream_ptr()), "sx_rgb_prefill_upsample_blur")
+    assert float((out.cpu() - ref).abs().max()) <= 2e-6

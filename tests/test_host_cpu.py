@@ -528,18 +528,18 @@ def test_screen_and_verify_recovers_the_exact_topk(seed, noise):
     want = O.attfind_select(exact, base, 5, 0.5)
     calls = []
 
-    def exact_columns(cols):
-        calls.append(len(cols))
-        return torch.from_numpy(exact).reshape(n, 2 * S, 2)[:, torch.tensor(cols)]
+    def exact_entries(latent_idx, columns):
+        calls.append(int(latent_idx.numel()))
+        return torch.from_numpy(exact).reshape(n, 2 * S, 2)[latent_idx, columns]
 
     def select(eff, b, k, thr):
         return O.attfind_select(eff.numpy(), b.numpy(), k, thr)
 
-    picks, merged, scores, info = attfind.screen_and_verify(torch.from_numpy(approx), torch.from_numpy(base), exact_columns,
+    picks, merged, scores, info = attfind.screen_and_verify(torch.from_numpy(approx), torch.from_numpy(base), exact_entries,
                                                             select, 5, 0.5, min_candidates=16)
     assert info["verified"], info
     assert picks == want[0] and merged == want[1]
     assert scores == want[2]
-    assert sum(calls) <= 2 * S and info["candidates"] == sum(calls)
+    assert sum(calls) == info["exact_evals"] <= 2 * S * n
     if noise <= 1e-2:
-        assert sum(calls) < 0.5 * 2 * S                                            # a fraction of the 2S columns
+        assert info["exact_evals"] < 0.25 * 2 * S * n                              # a fraction of the N x 2S entries
