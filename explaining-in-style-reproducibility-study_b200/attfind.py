@@ -278,14 +278,20 @@ def _exact_entries(G: Generator, classifier, noise: torch.Tensor, styles_all: to
     plan.reserve(max_batch, precision)
     stream = N.stream_ptr()
     styles_b = torch.empty(max_batch, row, device=dev, dtype=torch.float32)
+    # every batch has exactly max_batch rows (the tail repeats the last pair): one shape for the classifier's cuDNN plans
+    # (with cudnn.benchmark each new batch size re-tunes ~20 fp32 convolutions: seconds per odd-sized tail, measured)
+    if n % max_batch:
+        pad = max_batch - n % max_batch
+        li = torch.cat([li, li[-1:].expand(pad)]).contiguous()
+        ci = torch.cat([ci, ci[-1:].expand(pad)]).contiguous()
     for j0 in range(0, n, max_batch):
         cnt = min(max_batch, n - j0)
         N.check(lib.sx_attfind_make_styles_pairs(styles_all.data_ptr(), styles_all.stride(0), minima.data_ptr(), maxima.data_ptr(),
-                                                 styles_b.data_ptr(), row, S, li[j0:].data_ptr(), ci[j0:].data_ptr(), cnt,
+                                                 styles_b.data_ptr(), row, S, li[j0:].data_ptr(), ci[j0:].data_ptr(), max_batch,
                                                  float(shift_size), stream), "sx_attfind_make_styles_pairs")
-        rgb = plan.forward(styles_b[:cnt], noise, precision=precision)
+        rgb = plan.forward(styles_b, noise, precision=precision)
         logits = classifier.classify_images(rgb).float()
-        out[j0: j0 + cnt] = logits - base_exact[li[j0: j0 + cnt].long()]
+        out[j0: j0 + cnt] = (logits - base_exact[li[j0: j0 + max_batch].long()])[:cnt]
     return out
 
 
@@ -458,8 +464,11 @@ def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: 
     base_loc = torch.empty(hi - lo, 2, device=dev, dtype=torch.float32)
     for i in range(lo, hi, max_batch):
         j = min(hi, i + max_batch)
-        rgb = plan.forward(styles_all[i:j].contiguous(), noise, precision=precision)
-        base_loc[i - lo: j - lo] = classifier.classify_images(rgb).float()
+        rows_b = styles_all[i:j]
+        if j - i < max_batch:                           # fixed batch shape (see _exact_entries)
+            rows_b = torch.cat([rows_b, rows_b[-1:].expand(max_batch - (j - i), -1)])
+        rgb = plan.forward(rows_b.contiguous(), noise, precision=precision)
+        base_loc[i - lo: j - lo] = classifier.classify_images(rgb).float()[: j - i]
     base_exact = gather_rows(base_loc, n_all)
 
     def exact_entries(latent_idx, columns):

@@ -693,7 +693,10 @@ static int selftest_ups_case(int B, int Ci, int Co, int H, float* max_err) {
       const float d = fabsf(__bfloat162float(oa[i]) - __bfloat162float(ob[i]));
       if (!(d <= m)) m = d;
     }
-    if (m != 0.f) rc = fail(SX_ECUDA, "selftest(ups) B=%d Ci=%d Co=%d H=%d: fused-upsample conv differs from upsample + conv by %g", B, Ci, Co, H, m);
+    // same MMA order in both kernels => bit-identical; when exactly one of the two runs the column-parity form (another
+    // fp32 summation order) the rounded bf16 outputs may differ by an ulp
+    const float allow = (tc::halo_par() & ~1) ? 0.02f : 0.f;
+    if (m > allow) rc = fail(SX_ECUDA, "selftest(ups) B=%d Ci=%d Co=%d H=%d: fused-upsample conv differs from upsample + conv by %g", B, Ci, Co, H, m);
     if (!(m <= *max_err)) *max_err = m;
   }
   cudaFree(dlow); cudaFree(dfull); cudaFree(dw); cudaFree(da); cudaFree(db);

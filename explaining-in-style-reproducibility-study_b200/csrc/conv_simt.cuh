@@ -7,14 +7,14 @@
 // GEMM view (reference Conv2DMod.forward ST:647-667 with the modulation moved to the activations):
 //   M = B*H*W pixels, N = Co, K = k*k*Ci;  A[m, (tap,ci)] = xmod[b, y+dy, x+dx, ci] (zero padded),
 //   B[(tap,ci), o] = W[o, ci, tap]  (packed [tap][Ci][Co], shared by the whole batch).
-// Tile 64x64x16, 256 threads, 4x4 register micro-tile, double-buffered shared memory.
+// 256 threads, register micro-tiles, double-buffered shared memory (tile configurations below).
 #pragma once
 
 #include "common.cuh"
 
 namespace sx {
 
-constexpr int SIMT_BM = 64, SIMT_BN = 64, SIMT_BK = 16, SIMT_THREADS = 256;
+constexpr int SIMT_BK = 16, SIMT_THREADS = 256;
 
 struct ConvSimtParams {
   const float* x;       // [Bx, H, W, Ci] NHWC, already modulated by (style+1)
@@ -24,16 +24,26 @@ struct ConvSimtParams {
   ConvEpilogue ep;
 };
 
+// Tile BM pixels x BN channels x 16, 256 threads, TM x TN register micro-tile.  Every output is the same sequential fp32
+// FMA chain over (tap, channel) whatever the tiling, so all configurations give bit-identical results:
+//   <128, 64, 8, 4>  large layers: 32 FMAs per 12 shared-memory floats (the 64 x 64 / 4 x 4 form: 16 per 8)
+//   <128, 32, 4, 4>  Co <= 32 (the 256 px layers of the generator; a 64-wide tile wasted half of its columns there)
+//   < 64, 64, 4, 4>  small launches (more CTAs)
+template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams p) {
-  __shared__ __align__(16) float As[2][SIMT_BK][SIMT_BM + 4];
-  __shared__ __align__(16) float Bs[2][SIMT_BK][SIMT_BN + 4];
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == SIMT_THREADS && TN == 4 && TM % 4 == 0 && BM % 64 == 0, "tile / thread layout");
+  constexpr int A_LD = BM / 64;                 // float4 A loads per thread and K chunk
+  constexpr int B_COLS = BN / 4;                // float4 columns of the B tile
+  __shared__ __align__(16) float As[2][SIMT_BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][SIMT_BK][BN + 4];
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid % TX, ty = tid / TX;
   const int HW = p.H * p.W;
   const long long M = (long long)p.B * HW;
-  const long long m0 = (long long)blockIdx.x * SIMT_BM;
-  const int n0 = blockIdx.y * SIMT_BN;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
   const int pad = (p.KS - 1) / 2;
   const int taps = p.KS * p.KS;
   const int kchunks = (p.Ci + SIMT_BK - 1) / SIMT_BK;
@@ -41,41 +51,52 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
   const bool ci_vec = (p.Ci & 3) == 0;
   const bool co_vec = (p.Co & 3) == 0;
 
-  // A loader: pixel a_pix of the tile, 4 channels starting at a_cg of the K chunk
+  // A loader: pixels a_pix + 64 l of the tile, 4 channels starting at a_cg of the K chunk
   const int a_pix = tid >> 2, a_cg = (tid & 3) * 4;
-  const long long a_m = m0 + a_pix;
-  const bool a_ok = a_m < M;
-  int a_b = 0, a_y = 0, a_x = 0;
-  if (a_ok) {
-    a_b = (int)(a_m / HW);
-    int r = (int)(a_m - (long long)a_b * HW);
-    a_y = r / p.W;
-    a_x = r - a_y * p.W;
+  bool a_ok[A_LD];
+  int a_y[A_LD], a_x[A_LD];
+  const float* a_base[A_LD];
+#pragma unroll
+  for (int l = 0; l < A_LD; ++l) {
+    const long long a_m = m0 + a_pix + 64 * l;
+    a_ok[l] = a_m < M;
+    int a_b = 0;
+    a_y[l] = a_x[l] = 0;
+    if (a_ok[l]) {
+      a_b = (int)(a_m / HW);
+      const int r = (int)(a_m - (long long)a_b * HW);
+      a_y[l] = r / p.W;
+      a_x[l] = r - a_y[l] * p.W;
+    }
+    a_base[l] = p.x + (long long)a_b * p.x_bstride;
   }
-  const float* a_base = p.x + (long long)a_b * p.x_bstride;
-  // B loader: K row b_kr of the chunk, 4 output channels starting at b_ng
-  const int b_kr = tid >> 4, b_ng = (tid & 15) * 4;
+  // B loader: K row b_kr of the chunk, 4 output channels starting at b_ng (threads beyond the tile idle)
+  const int b_kr = tid / B_COLS, b_ng = (tid % B_COLS) * 4;
+  const bool b_active = b_kr < SIMT_BK;
 
-  float a_reg[4], b_reg[4];
+  float a_reg[A_LD][4], b_reg[4];
   auto load_tiles = [&](int it) {
     const int tap = it / kchunks;
     const int c0 = (it - tap * kchunks) * SIMT_BK;
     const int dy = tap / p.KS - pad, dx = tap % p.KS - pad;
     // ---- A
-    const int sy = a_y + dy, sx_ = a_x + dx;
-    const bool in = a_ok && sy >= 0 && sy < p.H && sx_ >= 0 && sx_ < p.W;
     const int c = c0 + a_cg;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a_reg[j] = 0.f;
-    if (in) {
-      const float* src = a_base + ((long long)sy * p.W + sx_) * p.Ci + c;
-      if (ci_vec && c + 3 < p.Ci) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(src));
-        a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
-      } else {
+    for (int l = 0; l < A_LD; ++l) {
+      const int sy = a_y[l] + dy, sx_ = a_x[l] + dx;
+      const bool in = a_ok[l] && sy >= 0 && sy < p.H && sx_ >= 0 && sx_ < p.W;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c + j < p.Ci) a_reg[j] = __ldg(src + j);
+      for (int j = 0; j < 4; ++j) a_reg[l][j] = 0.f;
+      if (in) {
+        const float* src = a_base[l] + ((long long)sy * p.W + sx_) * p.Ci + c;
+        if (ci_vec && c + 3 < p.Ci) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(src));
+          a_reg[l][0] = v.x; a_reg[l][1] = v.y; a_reg[l][2] = v.z; a_reg[l][3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < p.Ci) a_reg[l][j] = __ldg(src + j);
+        }
       }
     }
     // ---- B
@@ -83,7 +104,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
     const int n = n0 + b_ng;
 #pragma unroll
     for (int j = 0; j < 4; ++j) b_reg[j] = 0.f;
-    if (kc < p.Ci) {
+    if (b_active && kc < p.Ci) {
       const float* src = p.wpk + ((long long)tap * p.Ci + kc) * p.Co + n;
       if (co_vec && n + 3 < p.Co) {
         float4 v = __ldg(reinterpret_cast<const float4*>(src));
@@ -97,15 +118,17 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
   };
   auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) As[buf][a_cg + j][a_pix] = a_reg[j];
-    *reinterpret_cast<float4*>(&Bs[buf][b_kr][b_ng]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
+    for (int l = 0; l < A_LD; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[buf][a_cg + j][a_pix + 64 * l] = a_reg[l][j];
+    if (b_active) *reinterpret_cast<float4*>(&Bs[buf][b_kr][b_ng]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
   };
 
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   load_tiles(0);
   store_tiles(0);
@@ -115,14 +138,18 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
     if (it + 1 < iters) load_tiles(it + 1);
 #pragma unroll
     for (int k = 0; k < SIMT_BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+      float av[TM];
+#pragma unroll
+      for (int i4 = 0; i4 < TM / 4; ++i4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4 * i4]);
+        av[4 * i4] = a.x; av[4 * i4 + 1] = a.y; av[4 * i4 + 2] = a.z; av[4 * i4 + 3] = a.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     if (it + 1 < iters) store_tiles(buf ^ 1);
     __syncthreads();
@@ -132,8 +159,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
   const ConvEpilogue& ep = p.ep;
   const int S = ep.noise_size;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + ty * TM + i;
     if (m >= M) continue;
     const int b = (int)(m / HW);
     const int r = (int)(m - (long long)b * HW);
@@ -141,7 +168,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
     float nz = 0.f;
     if (ep.noise) nz = __ldg(ep.noise + (long long)(ep.noise_batch == 1 ? 0 : b) * S * S + (long long)x * S + y);
     float v[4], vr[4];
-    const int o0 = n0 + tx * 4;
+    const int o0 = n0 + tx * TN;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int o = o0 + j;
@@ -187,8 +214,18 @@ inline int launch_conv_simt(const ConvSimtParams& p, cudaStream_t stream) {
   SX_REQUIRE(p.KS == 1 || p.KS == 3, "conv_simt: kernel size %d not supported (1 or 3)", p.KS);
   const long long M = (long long)p.B * p.H * p.W;
   if (M == 0 || p.Co == 0) return SX_OK;
-  dim3 grid((unsigned)((M + SIMT_BM - 1) / SIMT_BM), (unsigned)((p.Co + SIMT_BN - 1) / SIMT_BN));
-  conv_simt_kernel<<<grid, SIMT_THREADS, 0, stream>>>(p);
+  static const bool old_tile = getenv("SX_SIMT_64") != nullptr;   // A/B: the 64 x 64 / 4 x 4 form everywhere
+  const long long ctas_big = ((M + 127) / 128) * ((p.Co + 63) / 64);
+  if (!old_tile && p.Co <= 32 && M >= 128 * 2 * num_sms()) {
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((p.Co + 31) / 32));
+    conv_simt_kernel<128, 32, 4, 4><<<grid, SIMT_THREADS, 0, stream>>>(p);
+  } else if (!old_tile && ctas_big >= 2 * num_sms()) {
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((p.Co + 63) / 64));
+    conv_simt_kernel<128, 64, 8, 4><<<grid, SIMT_THREADS, 0, stream>>>(p);
+  } else {
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.Co + 63) / 64));
+    conv_simt_kernel<64, 64, 4, 4><<<grid, SIMT_THREADS, 0, stream>>>(p);
+  }
   SX_CHECK_LAUNCH();
   return SX_OK;
 }

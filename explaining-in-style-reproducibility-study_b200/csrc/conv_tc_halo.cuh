@@ -53,8 +53,20 @@ constexpr int halo_pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 
 // thread drains pixel r of all TPS tiles in one pass, so each per-channel table value it fetches from shared memory
 // (a broadcast LDS: 128 threads read the same word) serves TPS pixels.  ncu: with TPS = 1 those table loads were 55-60 %
 // of the shared-memory wavefronts of the narrow layers, whose L1/shared data pipe ran at 80-85 % -- the actual bound.
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS, int SETS, int UPS_WARPS, int TPS, int NMMA>
+//
+// PAR (column-parity form, for the Co <= 64 layers whose tcgen05.mma is paced by the shared-memory read of its A operand:
+// 4 KB per M128 x K16 instruction whatever N is): a super-tile is 16 rows x 16 pixels and TMEM lane r = (row yy, coarse
+// column xc) owns the TWO pixels x0 + 2 xc + delta.  out[2 xc + delta] = sum_kx W[kx] in[2 xc + delta + kx - 1]: the input
+// column 2 xc + u - 1 (u = 0..3) feeds (delta, kx) = (0, u) and (1, u - 1), so ONE A operand per (ky, u) -- 4 instead of
+// 6 per filter row -- serves both pixels: u = 1, 2 as a single N = 2 Co instruction whose B operand is two ADJACENT
+// resident weight tiles (the tiles of a filter row are stored kx = 2, 1, 0), u = 0 / 3 as N = Co instructions into the
+// delta = 0 / 1 half of the accumulator.  The stride-2 column sampling comes from TMA (elementStrides = {1, 2, 1, 1}:
+// two 18 x 9 boxes per stage, odd columns x0 - 1 + 2 m and even columns x0 + 2 m) or, with the fused upsample, from the
+// producer warps, which already compute even and odd output columns separately.
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool UPS, int SETS, int UPS_WARPS, int TPS, int NMMA,
+          bool PAR = false>
 struct HaloCfg {
+  static_assert(!PAR || (TPS == 2 && RESIDENT_B), "the parity form owns two pixels per lane and keeps the weights resident");
   static_assert(SETS >= 2 && SETS <= 4, "2..4 accumulator slots / epilogue sets");
   static_assert(TPS == 1 || TPS == 2, "tiles per accumulator slot (W >= 16 guarantees two tiles per tile row)");
   static_assert(NMMA == 1 || NMMA == 2, "one or two MMA-issuing warps");
@@ -69,10 +81,14 @@ struct HaloCfg {
   static constexpr int kUpsThreads = UPS ? 32 * UPS_WARPS : 0;
   static constexpr int kFrontThreads = 128;   // warp 0 TMA, warps 1..NMMA MMA issuers, the rest of the first four idle (sets stay 4-aligned)
   static constexpr int kThreads = kFrontThreads + kEpiThreads + kUpsThreads;
-  static constexpr int kSrcBytes = UPS_SRC_W * UPS_SRC_H * kRowBytes;   // one source box (7680 B at BLOCK_K = 64)
+  static constexpr int kSrcW = PAR ? HALO_BW + 2 : UPS_SRC_W;           // low-res source columns: 10 for a 16-pixel super-tile
+  static constexpr int kSrcBytes = kSrcW * UPS_SRC_H * kRowBytes;       // one source box (7680 B at BLOCK_K = 64; PAR: 12800 B)
   static constexpr int kSrcRegion = UPS ? UPS_S_STAGES * kSrcBytes : 0;
-  static constexpr int kATx = HALO_ROWS * kRowBytes;              // bytes one halo box delivers
-  static constexpr int kABytes = (kATx + 1023) / 1024 * 1024;     // stage stride (keeps every stage 1024 B aligned)
+  static constexpr int kHaloW = PAR ? HALO_BW + 1 : HALO_W;             // pixel rows per halo row in a box (PAR: 9 per lattice)
+  static constexpr int kBoxRows = kHaloW * HALO_H;
+  static constexpr int kBoxBytes = (kBoxRows * kRowBytes + 1023) / 1024 * 1024;   // every box 1024 B aligned (swizzle phase)
+  static constexpr int kATx = (PAR ? 2 : 1) * kBoxRows * kRowBytes;     // bytes one stage receives
+  static constexpr int kABytes = (PAR ? 2 : 1) * kBoxBytes;             // stage stride
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;           // weights of one (channel chunk, tap)
   static constexpr int kSlotCols = TPS * BLOCK_N;
   static constexpr int kTmemCols = halo_pow2_cols(SETS * kSlotCols);
@@ -162,10 +178,10 @@ __device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
 }
 
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS, int SETS, int UPS_WARPS,
-          int TPS, int NMMA>
-__global__ void __launch_bounds__(HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA>::kThreads, 1)
+          int TPS, int NMMA, bool PAR = false>
+__global__ void __launch_bounds__(HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA, PAR>::kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvHaloParams p) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA>;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA, PAR>;
   static_assert(!UPS || BLOCK_K == 64, "the fused-upsample producer writes the SWIZZLE_128B layout");
   extern __shared__ uint8_t smem_raw[];
   // offset arithmetic on the __shared__ array (not an integer round trip) keeps the shared address space known to the
@@ -242,7 +258,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (elect_one()) {
           mbar_arrive_expect_tx(&b_full[0], (uint32_t)(p.num_b_tiles * Cfg::kBBytes));
           for (int i = 0; i < p.num_b_tiles; ++i) {
-            const int chunk = i / 9, tap = i - chunk * 9;
+            const int chunk = i / 9;
+            int tap = i - chunk * 9;
+            if (PAR) tap = (tap / 3) * 3 + (2 - tap % 3);   // the tiles of a filter row lie kx = 2, 1, 0 (see the MMA issuer)
             tma_load_2d(smem_b + (size_t)i * Cfg::kBBytes, &tmap_b, &b_full[0], tap * p.Ci + chunk * BLOCK_K, n0);
           }
         }
@@ -251,7 +269,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // ring positions per half (index = tile parity); the source-box ring of the fused upsample is one in-order ring
       int as2[2] = {0, 0}, bs2[2] = {0, 0}, ss = 0;
       uint32_t aph2[2] = {0, 0}, bph2[2] = {0, 0}, sph = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += PAR ? 2 : 1) {   // PAR: one stage fill per 16-pixel super-tile
         const int b = tile >> p.tpb_shift;
         const int tr = tile - (b << p.tpb_shift);
         const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
@@ -266,7 +284,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_wait(&s_empty[ss], sph ^ 1, 10);
             if (elect_one()) {
               if (chunk == 0) SX_TRACE(0, tile - tile_begin);
-              mbar_arrive_expect_tx(&s_full[ss], Cfg::kSrcBytes);
+              mbar_arrive_expect_tx(&s_full[ss], Cfg::kSrcBytes);   // (PAR: the tensor map's box is 10 columns wide)
               tma_load_4d(smem_src + ss * Cfg::kSrcBytes, &tmap_a, &s_full[ss], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
             }
             __syncwarp();
@@ -281,6 +299,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               } else {
                 mbar_arrive_expect_tx(&a_full[st], Cfg::kATx);
                 tma_load_4d(smem_a + st * Cfg::kABytes, &tmap_a, &a_full[st], chunk * BLOCK_K, x0 - 1, y0 - 1, b);
+                if (PAR)   // the map samples every other column: this box holds x0 - 1 + 2 m, the second one x0 + 2 m
+                  tma_load_4d(smem_a + st * Cfg::kABytes + Cfg::kBoxBytes, &tmap_a, &a_full[st], chunk * BLOCK_K, x0, y0 - 1, b);
               }
             }
             __syncwarp();
@@ -314,7 +334,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     {
       const int mw = warp_id - 1;
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
-      constexpr uint32_t sbo = HALO_W * Cfg::kRowBytes;
+      constexpr uint32_t idesc2 = make_idesc(2 * BLOCK_N);   // PAR: both pixels of a lane in one instruction
+      constexpr uint32_t sbo = Cfg::kHaloW * Cfg::kRowBytes;
       if (RESIDENT_B) {
         mbar_wait(&b_full[0], 0, 12);
         tc_fence_after();
@@ -333,7 +354,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t accph = (uint32_t)(si / SETS) & 1u;
         mbar_wait(&tmem_empty[acc], accph ^ 1, 13);   // this slot's epilogue set has drained the accumulators
         tc_fence_after();
-        for (int sub = 0; sub < tps; ++sub) {
+        for (int sub = 0; sub < (PAR ? 1 : tps); ++sub) {
           const int ti = (si << tps_shift) + sub;
           (void)ti;
           if (lane == 0) SX_TRACE(1, ti);
@@ -345,7 +366,40 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // descriptors of tap 0; every other tap / k step is this plus a compile-time constant (fully unrolled)
             const uint64_t da0 = make_smem_desc_sbo<BLOCK_K>(a_base0 + (uint32_t)(as * Cfg::kABytes), sbo);
             const uint64_t db_res = make_smem_desc<BLOCK_K>(b_base0 + (uint32_t)(chunk * 9 * Cfg::kBBytes));
-            if (RESIDENT_B) {
+            if constexpr (PAR) {
+              // column-parity form: per filter row 4 A operands (input columns 2 xc + u - 1, u = 0..3) instead of 6.
+              // box 0 = odd lattice (columns x0 - 1 + 2 m), box 1 = even lattice (x0 + 2 m); weight tiles kx = 2, 1, 0.
+              //   u = 3: even, m = xc + 1, W[kx=2]            -> delta = 1 half      (N = Co)
+              //   u = 0: odd,  m = xc,     W[kx=0]            -> delta = 0 half      (N = Co)
+              //   u = 1: even, m = xc,     W[kx=1] | W[kx=0]  -> both halves         (N = 2 Co)
+              //   u = 2: odd,  m = xc + 1, W[kx=2] | W[kx=1]  -> both halves         (N = 2 Co)
+              // the two N = Co instructions come first so that the very first write of each half can overwrite
+              if (elect_one()) {
+                if (!(dbg & 2)) {
+                  const uint64_t da1 = da0 + (uint64_t)(Cfg::kBoxBytes >> 4);
+                  constexpr uint64_t mshift = (uint64_t)(Cfg::kRowBytes >> 4);
+                  constexpr uint64_t btile = (uint64_t)(Cfg::kBBytes >> 4);
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky) {
+                    const uint64_t row = (uint64_t)((ky * Cfg::kHaloW * Cfg::kRowBytes) >> 4);
+                    const uint64_t dbk = db_res + (uint64_t)(ky * 3) * btile;   // tile of (ky, kx = 2)
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                      const uint32_t first = (chunk | ky | k) != 0 ? 1u : 0u;
+                      umma_bf16(d_tmem + BLOCK_N, da1 + row + mshift + (uint64_t)(2 * k), dbk + (uint64_t)(2 * k), idesc, first);
+                      umma_bf16(d_tmem, da0 + row + (uint64_t)(2 * k), dbk + 2 * btile + (uint64_t)(2 * k), idesc, first);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                      umma_bf16(d_tmem, da1 + row + (uint64_t)(2 * k), dbk + btile + (uint64_t)(2 * k), idesc2, 1u);
+                      umma_bf16(d_tmem, da0 + row + mshift + (uint64_t)(2 * k), dbk + (uint64_t)(2 * k), idesc2, 1u);
+                    }
+                  }
+                }
+                umma_commit(&my_a_empty[as]);
+              }
+              __syncwarp();
+            } else if (RESIDENT_B) {
               // weights resident: nothing to wait for inside the chunk -- one election, 9 x BLOCK_K/16 back-to-back MMAs
               if (elect_one()) {
                 if (!(dbg & 2)) {
@@ -403,32 +457,37 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr int CGS = 64 / CH;                    // channel groups per pixel row
     const int pt = threadIdx.x - (Cfg::kFrontThreads + Cfg::kEpiThreads);
     const int cg = pt % CGS;
-    const int unit = pt / CGS;                  // 0..15; unit 15 has no work
-    const int j = unit % 5;                     // halo columns 2j, 2j+1 <- source columns j, j+1
-    const int seg = unit / 5;                   // halo rows 6seg .. 6seg+5 <- source rows 3seg .. 3seg+3
+    // work units: (column pair j, row segment seg); 5 x 3 for an 8-pixel tile, 9 x 3 for the 16-pixel PAR super-tile.
+    // A thread takes units pt / CGS, pt / CGS + units-per-pass, ...
+    constexpr int kPairs = PAR ? HALO_BW + 1 : HALO_W / 2;           // halo columns 2j, 2j+1 <- source columns j, j+1
+    constexpr int kUnits = 3 * kPairs;
+    constexpr int kUnitsPerPass = Cfg::kUpsThreads / CGS;
     const uint32_t cbyte = (uint32_t)(cg * CH * 2);            // byte offset of the channel group inside a 128-byte pixel row
     const uint32_t c16 = cbyte >> 4, cin = cbyte & 15u;        // 16-byte chunk index (swizzled), offset inside the chunk
     const uint64_t q25 = pk2(0.25f, 0.25f), q75 = pk2(0.75f, 0.75f);
     int as2[2] = {0, 0}, ss = 0;     // A-ring position per half (tile parity), one in-order source-box ring
     uint32_t aph2[2] = {0, 0}, sph = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = tile_begin; tile < tile_end; tile += PAR ? 2 : 1) {
       const int b = tile >> p.tpb_shift;
       const int tr = tile - (b << p.tpb_shift);
       const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
       const int rg = NMMA == 2 ? (((tile - tile_begin) >> tps_shift) & 1) : 0;
       int as = rg ? as2[1] : as2[0];
       uint32_t aph = rg ? aph2[1] : aph2[0];
-      const bool left = tx == 0, right = tx == p.tiles_x - 1, top = ty == 0, bottom = ty == p.tiles_y - 1;
-      const int lo_c = left ? 1 : 0, hi_c = right ? UPS_SRC_W - 2 : UPS_SRC_W - 1;
+      const bool left = tx == 0, right = tx + (PAR ? 2 : 1) == p.tiles_x, top = ty == 0, bottom = ty == p.tiles_y - 1;
+      const int lo_c = left ? 1 : 0, hi_c = right ? Cfg::kSrcW - 2 : Cfg::kSrcW - 1;
       const int lo_r = top ? 1 : 0, hi_r = bottom ? UPS_SRC_H - 2 : UPS_SRC_H - 1;
-      const int c0 = min(max(j, lo_c), hi_c), c1 = min(max(j + 1, lo_c), hi_c);
-      const bool zero_e = left && j == 0;        // halo column 0 is outside the image
-      const bool zero_o = right && j == 4;       // halo column 9 is outside the image
       for (int chunk = 0; chunk < p.kchunks; ++chunk) {
         const int st = rg * Cfg::kAHalf + as;
         mbar_wait(&s_full[ss], sph, 17);
         mbar_wait(&a_empty[st], aph ^ 1, 18);
-        if (seg < 3) {
+#pragma unroll 1
+        for (int unit = pt / CGS; unit < kUnits; unit += kUnitsPerPass) {
+          const int j = unit % kPairs;                // halo columns 2j, 2j+1 <- source columns j, j+1
+          const int seg = unit / kPairs;              // halo rows 6seg .. 6seg+5 <- source rows 3seg .. 3seg+3
+          const int c0 = min(max(j, lo_c), hi_c), c1 = min(max(j + 1, lo_c), hi_c);
+          const bool zero_e = left && j == 0;                 // halo column 0 is outside the image
+          const bool zero_o = right && j == kPairs - 1;       // the last halo column is outside the image
           const uint8_t* src = smem_src + ss * Cfg::kSrcBytes + cbyte;
           uint8_t* dst = smem_a + st * Cfg::kABytes + cin;
           uint64_t he0[NW], ho0[NW], he1[NW], ho1[NW];
@@ -444,8 +503,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           auto hrow = [&](int r, uint64_t* he, uint64_t* ho) {
             const int rr = min(max(r, lo_r), hi_r);
             uint32_t a[NW], c[NW];
-            ldv(src + (rr * UPS_SRC_W + c0) * Cfg::kRowBytes, a);
-            ldv(src + (rr * UPS_SRC_W + c1) * Cfg::kRowBytes, c);
+            ldv(src + (rr * Cfg::kSrcW + c0) * Cfg::kRowBytes, a);
+            ldv(src + (rr * Cfg::kSrcW + c1) * Cfg::kRowBytes, c);
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
               const uint64_t a2 = bf2_to_f2(a[k]), c2 = bf2_to_f2(c[k]);
@@ -454,11 +513,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           };
           auto put = [&](int hy, int hx, const uint64_t* v, bool zero) {
-            const int pix = hy * HALO_W + hx;
+            // PAR: halo column hx <-> image column x0 - 1 + hx lives in lattice box hx & 1 at coarse column hx >> 1
+            const int pix = PAR ? hy * Cfg::kHaloW + (hx >> 1) : hy * HALO_W + hx;
             uint32_t w[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k) w[k] = zero ? 0u : f2_to_bf2(v[k]);
-            uint8_t* d = dst + pix * Cfg::kRowBytes + ((c16 ^ (uint32_t)(pix & 7)) << 4);
+            uint8_t* d = dst + (PAR ? (hx & 1) * Cfg::kBoxBytes : 0) + pix * Cfg::kRowBytes + ((c16 ^ (uint32_t)(pix & 7)) << 4);
             if constexpr (CH == 8) *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
             else *reinterpret_cast<uint2*>(d) = make_uint2(w[0], w[1]);
           };
@@ -504,6 +564,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp_id & 3;          // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;        // tile row = TMEM lane
     const int yy = r >> 3, xx = r & 7;
+    // pixel j of this thread: x + JSTEP * j.  Plain: the same lane of TPS tiles 8 pixels apart; PAR: lane (yy, xc) owns the
+    // two adjacent pixels x0 + 2 xc + {0, 1} of its 16-pixel super-tile
+    constexpr int JSTEP = PAR ? 1 : HALO_BW;
+    constexpr int XSCALE = PAR ? 2 : 1;
     float* tab = s_tab + set * (10 * BLOCK_N);
     const uint32_t bar_id = 1u + (uint32_t)set;
     const uint32_t HW = (uint32_t)(p.H * p.W);
@@ -514,7 +578,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       b = tile >> p.tpb_shift;
       const int tr = tile - (b << p.tpb_shift);
       const int ty = tr >> p.tx_shift, tx = tr - (ty << p.tx_shift);
-      x = tx * HALO_BW + xx;
+      x = tx * HALO_BW + XSCALE * xx;
       y = ty * HALO_BH + yy;
     };
     // 32-bit element offsets (the launcher checks every tensor is below 2^31 elements)
@@ -556,7 +620,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float nz[TPS];
     auto load_noises = [&](int b_, int x_, int y_, float* nzv) {
 #pragma unroll
-      for (int j = 0; j < TPS; ++j) nzv[j] = j < tps ? load_noise(b_, x_ + HALO_BW * j, y_) : 0.f;
+      for (int j = 0; j < TPS; ++j) nzv[j] = j < tps ? load_noise(b_, x_ + JSTEP * j, y_) : 0.f;
     };
     if (sup < super_end) {
       tile_coords(sup * tps, b, x, y);
@@ -589,7 +653,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
       for (int j = 0; j < TPS; ++j) {
         rgb_acc[j][0] = rgb_acc[j][1] = rgb_acc[j][2] = 0.f;
-        if (j < tps) load_rgb_prev(b, x + HALO_BW * j, y, rgb_acc[j]);
+        if (j < tps) load_rgb_prev(b, x + JSTEP * j, y, rgb_acc[j]);
       }
       if (et == 0) SX_TRACE(6, sup - super_begin);
       mbar_wait(&tmem_full[set], accph, 16);
@@ -603,7 +667,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int j = 0; j < TPS; ++j) racc[j][0] = racc[j][1] = racc[j][2] = 0ull;
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out) + ((size_t)pix * (uint32_t)p.Co + (uint32_t)n0);
         __nv_bfloat16* rawp = reinterpret_cast<__nv_bfloat16*>(ep.out_raw) + ((size_t)pix * (uint32_t)p.Co + (uint32_t)n0);
-        const uint32_t jstride = (uint32_t)(HALO_BW * p.Co);   // elements between this thread's pixels of consecutive tiles
+        const uint32_t jstride = (uint32_t)(JSTEP * p.Co);   // elements between this thread's pixels j and j + 1
         // CW columns per pass, double-buffered: the TMEM loads of pass k + 1 are in flight during the math of pass k.
         // The register budget (threads per CTA) picks the width.
         constexpr int CW = Cfg::kThreads <= 384 ? 16 : 8;
@@ -684,8 +748,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
         for (int j = 0; j < TPS; ++j) {
           if (j >= tps) break;
-          const int xj = x + HALO_BW * j;
-          const size_t pixj = (size_t)pix + (size_t)(HALO_BW * j);
+          const int xj = x + JSTEP * j;
+          const size_t pixj = (size_t)pix + (size_t)(JSTEP * j);
 #pragma unroll 1
           for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
             uint32_t v[8];
@@ -730,7 +794,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
         for (int j = 0; j < TPS; ++j) {
           if (j < tps) {
-            float* dst = ep.rgb_out + roff + HALO_BW * j;
+            float* dst = ep.rgb_out + roff + JSTEP * j;
             dst[0] = rgb_acc[j][0];
             dst[HW] = rgb_acc[j][1];
             dst[2u * HW] = rgb_acc[j][2];
@@ -762,9 +826,9 @@ inline bool halo_shape_supported(int Ci, int Co, int H, int W) {
 
 // x: the conv input [B,H,W,Ci] -- or, for UPS, the low-resolution tensor [B,H/2,W/2,Ci] the kernel upsamples itself
 template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, bool FUSE_RGB, bool UPS, int SETS, int UPS_WARPS, int TPS,
-          int NMMA>
+          int NMMA, bool PAR = false>
 int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA>;
+  using Cfg = HaloCfg<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, UPS, SETS, UPS_WARPS, TPS, NMMA, PAR>;
   // a super-tile never leaves its sample or its tile row: TPS divides tiles_x (a power of two >= 2, since W >= 16)
   if (p.tiles_x % TPS != 0) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %d tiles per row is not a multiple of %d", p.tiles_x, TPS);
   p.tps = TPS;
@@ -779,8 +843,10 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
     const int IH = UPS ? p.H / 2 : p.H, IW = UPS ? p.W / 2 : p.W;
     cuuint64_t gdim[4] = {(cuuint64_t)p.Ci, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)p.B};
     cuuint64_t gstr[3] = {(cuuint64_t)p.Ci * 2, (cuuint64_t)IW * p.Ci * 2, (cuuint64_t)IH * IW * p.Ci * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(UPS ? UPS_SRC_W : HALO_W), (cuuint32_t)(UPS ? UPS_SRC_H : HALO_H), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // PAR without the fused upsample: every other column (traversal stride 2) over a span of 17 = 9 columns per box
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(UPS ? Cfg::kSrcW : (PAR ? 2 * Cfg::kHaloW - 1 : HALO_W)),
+                         (cuuint32_t)(UPS ? UPS_SRC_H : HALO_H), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)((PAR && !UPS) ? 2 : 1), 1, 1};
     CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(x), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, UPS ? CU_TENSOR_MAP_SWIZZLE_NONE : swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -796,7 +862,7 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SX_ECUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS, SETS, UPS_WARPS, TPS, NMMA>;
+  auto kern = conv_tc_halo_kernel<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, FUSE_RGB, UPS, SETS, UPS_WARPS, TPS, NMMA, PAR>;
   const size_t smem = Cfg::smem_bytes(p.num_b_tiles);
   if (smem > 227 * 1024) return fail(SX_EUNSUPPORTED, "conv_tc_halo: %zu bytes of shared memory needed", smem);
   static size_t configured = 0;
@@ -863,10 +929,10 @@ int launch_conv_halo_cfg2(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvH
 }
 
 // plain (no fused upsample) configurations: ToRGB fusion is a run-time property of the epilogue descriptor
-template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, int SETS, int TPS, int NMMA>
+template <int BLOCK_N, int BLOCK_K, int A_STAGES, int B_STAGES, bool RESIDENT_B, int SETS, int TPS, int NMMA, bool PAR = false>
 int launch_conv_halo_cfg(const __nv_bfloat16* x, const __nv_bfloat16* wk, ConvHaloParams p, cudaStream_t stream) {
-  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false, SETS, 4, TPS, NMMA>(x, wk, p, stream);
-  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false, SETS, 4, TPS, NMMA>(x, wk, p, stream);
+  if (p.ep.rgb_style) return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, true, false, SETS, 4, TPS, NMMA, PAR>(x, wk, p, stream);
+  return launch_conv_halo_cfg2<BLOCK_N, BLOCK_K, A_STAGES, B_STAGES, RESIDENT_B, false, false, SETS, 4, TPS, NMMA, PAR>(x, wk, p, stream);
 }
 
 inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int bk, const ConvEpilogue& ep) {
@@ -891,8 +957,18 @@ inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int 
 // SX_HALO_VARIANT (bitmask, tuning experiments): 1 = the 32 -> 32 layers run 2 epilogue sets (wide passes) instead of 4;
 // 2 = the 64 -> 64 layers run 2 sets x 2 tiles with two MMA warps instead of 4 sets x 1 tile with one;
 // 4 = the fused-upsample 128 -> 64 layer runs 2 tiles per slot with two MMA warps;
-// 8 = the weight-streaming Co = 128 layers run an 8-deep weight ring (3 activation stages); 16 = 10-deep (2 activation stages)
+// 8 = the weight-streaming Co = 128 layers run the old 4-deep weight ring instead of 8
 // SX_HALO_MAX_CO: plain (non-upsample) layers wider than this go to conv_tc_kernel instead (A/B of the two kernels)
+// SX_HALO_PAR (bitmask, default 1): layers that run the column-parity form.  Measured at 256 px, batch 256 (profiles/README.md
+// r02d/e): 1 = 32 -> 32 (+ToRGB): 0.615 -> 0.551 ms (default ON); 2 = 64 -> 64 (+ToRGB) with 32-channel chunks x 4 stages:
+// 0.371 -> 0.492 ms (two pixels per lane at N = 64 spill in the ToRGB epilogue at the 96-register budget of 640 threads;
+// 3 stages of 64 channels with one MMA warp: 0.505); 4 = fused-upsample 64 -> 32 with 3 stages / one MMA warp: 0.853 ->
+// 0.835 ms (2 stages / two MMA warps: 1.04) -- that layer is issue-bound on its upsample producers + epilogue (ncu: 65 %
+// issue-active), not on the operand reads.  2 and 4 stay selectable for A/B runs; the GPU tests cover them (SX_HALO_PAR=7).
+inline int halo_par() {
+  static const int v = getenv("SX_HALO_PAR") ? atoi(getenv("SX_HALO_PAR")) : 1;
+  return v;
+}
 inline int halo_variant() {
   static const int v = getenv("SX_HALO_VARIANT") ? atoi(getenv("SX_HALO_VARIANT")) : 0;
   return v;
@@ -913,10 +989,15 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   //                                                                    N   K  A  B  resident SETS TPS MMA-warps
   if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 4, 2, true, 4, 2, 2>(x, wk, p, stream);
   if (Co == 32 && bk == 32 && resident) {
+    // column-parity form (SX_HALO_PAR bit 1): 4 stages of two 11 KB lattice boxes
+    if ((halo_par() & 1) && W >= 16) return launch_conv_halo_cfg<32, 32, 4, 2, true, 4, 2, 2, true>(x, wk, p, stream);
     if (halo_variant() & 1) return launch_conv_halo_cfg<32, 32, 8, 2, true, 2, 2, 2>(x, wk, p, stream);
     return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2>(x, wk, p, stream);
   }
   if (Co == 64 && bk == 64 && resident) {
+    // column-parity form (SX_HALO_PAR bit 2): 2 accumulator slots of 2 x 64 columns per set ... 4 sets x 128 = 512 columns
+    if ((halo_par() & 2) && W >= 16)    // 32-channel chunks: four 22 KB stages instead of two 43 KB ones
+      return launch_conv_halo_cfg<64, 32, 4, 2, true, 4, 2, 2, true>(x, wk, make_halo_params(B, Ci, Co, H, W, 32, ep), stream);
     if (halo_variant() & 2) return launch_conv_halo_cfg<64, 64, 4, 2, true, 2, 2, 2>(x, wk, p, stream);
     return launch_conv_halo_cfg<64, 64, 4, 2, true, 4, 1, 1>(x, wk, p, stream);
   }
@@ -924,9 +1005,10 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   if (Co == 64 && bk == 64 && weight_bytes <= 150 * 1024) return launch_conv_halo_cfg<64, 64, 2, 2, true, 4, 1, 1>(x, wk, p, stream);
   if (Co == 64 && bk == 64) return launch_conv_halo_cfg<64, 64, 3, 6, false, 4, 1, 1>(x, wk, p, stream);
   if (Co == 128 && bk == 64) {
-    if (halo_variant() & 8) return launch_conv_halo_cfg<128, 64, 3, 8, false, 2, 2, 1>(x, wk, p, stream);
-    if (halo_variant() & 16) return launch_conv_halo_cfg<128, 64, 2, 10, false, 2, 2, 1>(x, wk, p, stream);
-    return launch_conv_halo_cfg<128, 64, 3, 4, false, 2, 2, 1>(x, wk, p, stream);
+    // 8-deep weight ring: with 4 stages (4 x 272 cycles of MMA = 0.57 us of look-ahead, about one loaded L2 round trip) the
+    // streamed weights arrived late: 256->128@64 1017 -> 1136 TFLOP/s, 128->128@64 1041 -> 1095 (profiles/README.md r02a)
+    if (halo_variant() & 8) return launch_conv_halo_cfg<128, 64, 3, 4, false, 2, 2, 1>(x, wk, p, stream);
+    return launch_conv_halo_cfg<128, 64, 3, 8, false, 2, 2, 1>(x, wk, p, stream);
   }
   *handled = false;
   return SX_OK;
@@ -948,15 +1030,15 @@ inline int launch_conv_halo_ups(const __nv_bfloat16* xlow, const __nv_bfloat16* 
   const ConvHaloParams p = make_halo_params(B, Ci, Co, H, W, 64, ep);
   const size_t weight_bytes = (size_t)9 * Ci * Co * 2;
   //                                              N   K  A  B  resident rgb   ups  SETS producer-warps TPS MMA-warps
+  if (Co == 32 && (halo_par() & 4)) return launch_conv_halo_cfg2<32, 64, 3, 2, true, false, true, 4, 8, 2, 1, true>(xlow, wk, p, stream);
   if (Co == 32) return launch_conv_halo_cfg2<32, 64, 4, 2, true, false, true, 4, 8, 2, 2>(xlow, wk, p, stream);
   if (Co == 64 && weight_bytes <= 150 * 1024) {
     if (halo_variant() & 4) return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 4, 8, 2, 2>(xlow, wk, p, stream);
     return launch_conv_halo_cfg2<64, 64, 2, 2, true, false, true, 4, 8, 1, 1>(xlow, wk, p, stream);
   }
   if (Co == 64) return launch_conv_halo_cfg2<64, 64, 2, 6, false, false, true, 4, 8, 1, 1>(xlow, wk, p, stream);
-  if (halo_variant() & 8) return launch_conv_halo_cfg2<128, 64, 3, 8, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
-  if (halo_variant() & 16) return launch_conv_halo_cfg2<128, 64, 2, 10, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
-  return launch_conv_halo_cfg2<128, 64, 3, 4, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  if (halo_variant() & 8) return launch_conv_halo_cfg2<128, 64, 3, 4, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
+  return launch_conv_halo_cfg2<128, 64, 3, 8, false, false, true, 2, 8, 2, 1>(xlow, wk, p, stream);
 }
 
 // bf16 Conv2DMod dispatch: the halo-reusing persistent kernel where it applies, the per-tap kernel otherwise.
