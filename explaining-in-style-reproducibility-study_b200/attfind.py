@@ -295,6 +295,18 @@ def _exact_entries(G: Generator, classifier, noise: torch.Tensor, styles_all: to
     return out
 
 
+def sharded_entries(evaluate, latent_idx: torch.Tensor, columns: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
+    """Split the (latent, column) pair list evenly over the ranks (contiguous shares, ``shard_range``), let this rank
+    ``evaluate(latent_idx_share, columns_share) -> [share, 2]`` its part and all-gather the parts back in order: every rank
+    returns the same [P, 2] tensor, each entry computed by exactly one rank."""
+    total = int(latent_idx.numel())
+    if world_size == 1:
+        return evaluate(latent_idx, columns)
+    from .dist import gather_effects
+    plo, phi = shard_range(total, rank, world_size)
+    return gather_effects(evaluate(latent_idx[plo:phi], columns[plo:phi]).contiguous(), total, world_size)
+
+
 def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_entries, select, num_indices: int = 5,
                       effect_threshold: float = 0.5, min_candidates: int = 32, band_sigmas: float = 8.0,
                       band_floor: float = 2.0, max_passes: int = 6):
@@ -472,11 +484,10 @@ def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: 
     base_exact = gather_rows(base_loc, n_all)
 
     def exact_entries(latent_idx, columns):
-        total = int(latent_idx.numel())
-        plo, phi = shard_range(total, rank, world_size)                            # this rank's share of the pair list
-        loc = _exact_entries(G, classifier, noise, styles_all, base_exact, minima, maxima, latent_idx[plo:phi], columns[plo:phi],
-                             shift_size, precision, max_batch)
-        return gather_rows(loc, total)
+        return sharded_entries(
+            lambda li, ci: _exact_entries(G, classifier, noise, styles_all, base_exact, minima, maxima, li, ci, shift_size,
+                                          precision, max_batch),
+            latent_idx, columns, rank, world_size)
 
     return screen_and_verify(approx, base_exact, exact_entries, attfind_select, num_indices, effect_threshold,
                              min_candidates, band_sigmas, band_floor, max_passes)

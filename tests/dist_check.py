@@ -46,6 +46,22 @@ for prec in ("fp32", "bf16"):
     gathered = [None] * world
     dist.all_gather_object(gathered, picks[1])
     assert all(g == gathered[0] for g in gathered)
+# the verification pass (attfind_verify_topk) sharded over the ranks: base logits by latent owner, the (latent, column) pair
+# list split evenly, small all-gathers -- must give every rank the picks, merged list and hybrid tensor of a one-rank run
+sweep = sx.attfind_sweep(G, Pool(), lat, noise, precision="bf16", max_batch=64, rank=rank, world_size=world)
+multi = sx.attfind_verify_topk(G, Pool(), lat, noise, sweep, 5, 0.5, precision="fp32", max_batch=32, rank=rank, world_size=world,
+                               min_candidates=8)
+one = sx.attfind_verify_topk(G, Pool(), lat, noise, sweep, 5, 0.5, precision="fp32", max_batch=32, min_candidates=8)
+assert multi[0] == one[0] and multi[1] == one[1], (rank, multi[:2], one[:2])
+assert multi[3]["exact_evals"] == one[3]["exact_evals"] and multi[3]["verified"] == one[3]["verified"]
+assert torch.equal(multi[3]["style_change"], one[3]["style_change"]) and torch.equal(multi[3]["base_prob"], one[3]["base_prob"])
+full32 = sx.attfind_sweep(G, Pool(), lat, noise, precision="fp32", max_batch=64)
+ref = sx.attfind_select(full32["style_change"], full32["base_prob"], 5, 0.5)
+exact_ok = multi[0] == ref[0] and multi[1] == ref[1]
+gathered = [None] * world
+dist.all_gather_object(gathered, (multi[0], multi[1]))
+assert all(g == gathered[0] for g in gathered)
 dist.barrier()
-print(f"rank {rank}/{world}: sharded sweep + all-gather == single-rank sweep (fp32, bf16); selection agrees")
+print(f"rank {rank}/{world}: sharded sweep + all-gather == single-rank sweep (fp32, bf16); selection agrees; sharded verification == "
+      f"one-rank verification ({multi[3]['exact_evals']} exact evals, verified={multi[3]['verified']}); picks == full fp32 sweep: {exact_ok}")
 dist.destroy_process_group()

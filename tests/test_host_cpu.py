@@ -150,6 +150,57 @@ def test_gather_effects_world_size_2_gloo(tmp_path, n):
     assert all("ok" in o for o in outs), outs
 
 
+GLOO_VERIFY_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import stylex_b200 as sx
+from stylex_b200 import dist as sxd, attfind
+from oracle import stylex_oracle as O
+rank, world, _ = sxd.init_from_env("gloo")
+rng = np.random.default_rng(5)
+n, S = 23, 150
+exact = torch.from_numpy((rng.normal(size=(n, 2, S, 2)) * 0.4).astype(np.float32))
+base = torch.from_numpy(rng.normal(size=(n, 2)).astype(np.float32))
+approx = exact + torch.from_numpy((rng.normal(size=(n, 2, S, 2)) * 0.02).astype(np.float32))
+calls = []
+def evaluate(li, ci):                      # this rank's share of the (latent, column) pairs
+    calls.append(int(li.numel()))
+    return exact.reshape(n, 2 * S, 2)[li, ci]
+def entries(li, ci):
+    return attfind.sharded_entries(evaluate, li, ci, rank, world)
+def select(eff, b, k, thr):
+    return O.attfind_select(eff.numpy(), b.numpy(), k, thr)
+picks, merged, scores, info = attfind.screen_and_verify(approx, base, entries, select, 5, 0.5, min_candidates=8)
+want = O.attfind_select(exact.numpy(), base.numpy(), 5, 0.5)
+assert info["verified"] and picks == want[0] and merged == want[1], (picks, want[0])
+total = torch.tensor([float(sum(calls))])
+dist.all_reduce(total)
+assert int(total.item()) == info["exact_evals"], (total, info["exact_evals"])       # every pair evaluated by exactly one rank
+assert abs(sum(calls) - info["exact_evals"] / world) <= 3 * info["passes"] + 3      # ... in even shares
+got = [None] * world
+dist.all_gather_object(got, (picks, merged))
+assert all(g == got[0] for g in got)
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharded_verification_world_size_2_gloo(tmp_path):
+    """the N > 1 path of attfind_verify_topk's host logic: the candidate (latent, column) pair list is split evenly over
+    the ranks, each pair evaluated once, the parts all-gathered in order; every rank ends with the exact picks."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_VERIFY_WORKER.format(root=ROOT))
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs), outs
+
+
 def test_classifier_wrappers_match_reference_semantics():
     """resize-to-224 + normalise (ResNet) / interpolate-to-image_size + normalise (MobileNet), raw logits out."""
     import torchvision
