@@ -18,8 +18,16 @@ Autograd (first slice): at module level every op is 
 forward AND first-order backward are native kernels (``csrc/conv_bwd.cuh``, ``csrc/bwd_ops.cuh``), fp32, deterministic.
 ``Generator.forward`` takes that path when gradients are being recorded; under ``torch.no_grad()`` (AttFind, rendering)
 it runs the fused plan, which records nothing.  With ``precision = "bf16"`` the 3x3 modulated convolutions run forward,
-dgrad and wgrad on the tcgen05 kernels (bf16 operands, fp32 accumulation).  Not twice differentiable (no path-length /
-gradient penalty yet).
+dgrad and wgrad on the tcgen05 kernels (bf16 operands, fp32 accumulation).
+
+Double backward (the path-length penalty ST:306-316 differentiates d(image)/d(styles) again; the gradient penalty ST:296-303
+does the same through the discriminator): ``Blur`` and the bilinear upsample are linear maps, so each is a pair of Functions
+(operator / adjoint) that are each other's backward -- differentiable to any order.  With ``Generator.double_backward = True``
+the generator runs ``_forward_dd``: Conv2DMod as ``d * conv(W, x * (s + 1))`` where the convolution with batch-shared weights
+is ``ConvSharedFunction`` (native FFMA kernel) whose backward is again a ``ConvSharedFunction`` (dgrad = conv with the flipped,
+transposed weights) plus ``ConvWgradFunction`` (native wgrad), whose own backward is two ``ConvSharedFunction``s: the pair is
+closed under differentiation.  The cheap glue (modulation, demodulation coefficients, noise, leaky-ReLU, the style affines)
+is plain torch in that mode.  The default training path stays the fused first-order Functions above.
 """
 from __future__ import annotations
 
@@ -111,29 +119,49 @@ def _up_bwd(g):
 
 
 class BlurFunction(torch.autograd.Function):
-    """Blur.forward ST:144-153 / its adjoint (reflected border taps fold back inside)."""
+    """Blur.forward ST:144-153.  A linear map: its backward is the adjoint (reflected border taps fold back inside), itself a
+    Function whose backward is this one -- differentiable to any order (the gradient penalty ST:296-303 needs the second)."""
 
     @staticmethod
     def forward(ctx, x):
         return _blur_fwd(x.detach())
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        return _blur_bwd(g)
+        return BlurAdjointFunction.apply(g)
+
+
+class BlurAdjointFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g):
+        return _blur_bwd(g.detach())
+
+    @staticmethod
+    def backward(ctx, gg):
+        return BlurFunction.apply(gg)
 
 
 class Upsample2xFunction(torch.autograd.Function):
-    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) ST:679 / its adjoint."""
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) ST:679; backward = the adjoint, whose backward is
+    the upsample again (linear map: differentiable to any order)."""
 
     @staticmethod
     def forward(ctx, x):
         return _up_fwd(x.detach())
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        return _up_bwd(g)
+        return Upsample2xAdjointFunction.apply(g)
+
+
+class Upsample2xAdjointFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g):
+        return _up_bwd(g.detach())
+
+    @staticmethod
+    def backward(ctx, gg):
+        return Upsample2xFunction.apply(gg)
 
 
 class LinearFunction(torch.autograd.Function):
@@ -338,6 +366,75 @@ class Conv2DModFunction(torch.autograd.Function):
         return gx, gy, gw, None, None, None
 
 
+class ConvSharedFunction(torch.autograd.Function):
+    """y = conv2d(x, W, padding=(k-1)//2) with weights shared by the whole batch (what Conv2DMod becomes once the modulation
+    sits on the activations), NCHW fp32, native FFMA kernel.  Closed under differentiation together with
+    ``ConvWgradFunction``: grad_x = conv(g, flip(W)^T) is another ConvSharedFunction, grad_W = wgrad(x, g)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        N.require_cuda(x, w)
+        xd, wd = N.f32c(x.detach()), N.f32c(w.detach())
+        ctx.save_for_backward(x, w)
+        zero_style = torch.zeros(xd.shape[0], xd.shape[1], device=xd.device, dtype=torch.float32)
+        return _conv2dmod_forward(xd, zero_style, wd, False, 1e-8, N.PREC_FP32)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvSharedFunction.apply(g, w.flip(2, 3).transpose(0, 1))
+        if ctx.needs_input_grad[1]:
+            gw = ConvWgradFunction.apply(x, g, w.shape[2])
+        return gx, gw
+
+
+class ConvWgradFunction(torch.autograd.Function):
+    """gW[o,i,ky,kx] = sum_{b,y,x} g[b,o,y,x] * x[b,i,y+ky-p,x+kx-p] (native wgrad kernels).  Bilinear in (x, g): its backward
+    w.r.t. x is conv(g, flip(gW_bar)^T), w.r.t. g is conv(x, gW_bar) -- both ConvSharedFunctions."""
+
+    @staticmethod
+    def forward(ctx, x, g, k):
+        N.require_cuda(x, g)
+        xd, gd = N.f32c(x.detach()), N.f32c(g.detach())
+        b, ci, h, wd = xd.shape
+        co = gd.shape[1]
+        ctx.save_for_backward(x, g)
+        lib = N.lib()
+        zero_style = torch.zeros(b, ci, device=xd.device, dtype=torch.float32)
+        w_dummy = torch.zeros(co, ci, k, k, device=xd.device, dtype=torch.float32)   # feeds the (discarded) dgrad
+        gx = torch.empty_like(xd)
+        gy = torch.empty_like(zero_style)
+        gw = torch.empty_like(w_dummy)
+        ws = _op_ws.get(lib.sx_conv2dmod_bwd_workspace_bytes(b, ci, co, h, wd, k, N.PREC_FP32), xd.device)
+        N.check(lib.sx_conv2dmod_bwd(xd.data_ptr(), w_dummy.data_ptr(), zero_style.data_ptr(), None, gd.data_ptr(), gx.data_ptr(),
+                                     gw.data_ptr(), gy.data_ptr(), b, ci, co, h, wd, k, 0, 1e-8, N.PREC_FP32, ws.data_ptr(),
+                                     ws.numel(), N.stream_ptr()), "sx_conv2dmod_bwd")
+        return gw
+
+    @staticmethod
+    def backward(ctx, gw_bar):
+        x, g = ctx.saved_tensors
+        gx = gg = None
+        if ctx.needs_input_grad[0]:
+            gx = ConvSharedFunction.apply(g, gw_bar.flip(2, 3).transpose(0, 1))
+        if ctx.needs_input_grad[1]:
+            gg = ConvSharedFunction.apply(x, gw_bar)
+        return gx, gg, None
+
+
+def conv2dmod_dd(x, y, weight, demod=True, eps=1e-8):
+    """Conv2DMod.forward ST:647-667 in its twice-differentiable form: out = d[b,o] * conv(W, x * (y + 1)),
+    d = rsqrt(((y + 1)^2) @ (sum_taps W^2)^T + eps)  (the identity the fused kernels use)."""
+    s = y + 1
+    out = ConvSharedFunction.apply(x * s[:, :, None, None], weight)
+    if demod:
+        d = torch.rsqrt((s * s) @ (weight * weight).sum(dim=(2, 3)).t() + eps)
+        out = out * d[:, :, None, None]
+    return out
+
+
 class RGBBlock(nn.Module):
     def __init__(self, latent_dim, input_channel, upsample, rgba=False):
         super().__init__()
@@ -354,9 +451,21 @@ class RGBBlock(nn.Module):
         ) if upsample else None
 
     def forward(self, x, prev_rgb, istyle):
+        if getattr(self, "double_backward", False):
+            return self._forward_dd(x, prev_rgb, istyle)
         style = linear(istyle, self.to_style.weight, self.to_style.bias)
         x = self.conv(x, style)
         return RGBTailFunction.apply(x, prev_rgb, exists(self.upsample))
+
+    def _forward_dd(self, x, prev_rgb, istyle):
+        """ST:618-629 out of twice-differentiable pieces."""
+        style = nn.functional.linear(istyle, self.to_style.weight, self.to_style.bias)
+        x = conv2dmod_dd(x, style, self.conv.weight, demod=False)
+        if exists(prev_rgb):
+            x = x + prev_rgb
+        if exists(self.upsample):
+            x = BlurFunction.apply(Upsample2xFunction.apply(x))
+        return x
 
 
 class GeneratorBlock(nn.Module):
@@ -382,6 +491,8 @@ class GeneratorBlock(nn.Module):
         self.to_rgb = RGBBlock(latent_dim, filters, upsample_rgb, rgba)
 
     def forward(self, x, prev_rgb, istyle, inoise):
+        if getattr(self, "double_backward", False):
+            return self._forward_dd(x, prev_rgb, istyle, inoise)
         if exists(self.upsample):
             x = upsample2x(x)
         style1 = linear(istyle, self.to_style1.weight, self.to_style1.bias)
@@ -391,6 +502,26 @@ class GeneratorBlock(nn.Module):
         style_coords = torch.cat([style1, style2], dim=-1)
         x = self.conv2(x, style2)
         x = noise_lrelu(x, inoise, self.to_noise2)
+        rgb = self.to_rgb(x, prev_rgb, istyle)
+        return x, rgb, style_coords
+
+    def _forward_dd(self, x, prev_rgb, istyle, inoise):
+        """ST:692-718 out of twice-differentiable pieces (native convolutions / upsample / blur, torch glue)."""
+        N.require_cuda(x, istyle, inoise)
+        lin = nn.functional.linear
+        if exists(self.upsample):
+            x = Upsample2xFunction.apply(x)
+        inoise = inoise[:, :x.shape[2], :x.shape[3], :]
+        noise1 = self.to_noise1(inoise).permute((0, 3, 2, 1))
+        noise2 = self.to_noise2(inoise).permute((0, 3, 2, 1))
+        style1 = lin(istyle, self.to_style1.weight, self.to_style1.bias)
+        x = conv2dmod_dd(x, style1, self.conv1.weight, True, self.conv1.eps)
+        x = nn.functional.leaky_relu(x + noise1, 0.2)
+        style2 = lin(istyle, self.to_style2.weight, self.to_style2.bias)
+        style_coords = torch.cat([style1, style2], dim=-1)
+        x = conv2dmod_dd(x, style2, self.conv2.weight, True, self.conv2.eps)
+        x = nn.functional.leaky_relu(x + noise2, 0.2)
+        self.to_rgb.double_backward = True
         rgb = self.to_rgb(x, prev_rgb, istyle)
         return x, rgb, style_coords
 
@@ -524,6 +655,7 @@ class Generator(nn.Module):
         self.latent_dim = latent_dim
         self.num_layers = int(log2(image_size) - 1)
         self.precision = "fp32"
+        self.double_backward = False     # True: the twice-differentiable composition (path-length penalty), see module docstring
 
         filters = [network_capacity * (2 ** (i + 1)) for i in range(self.num_layers)][::-1]
 
@@ -581,8 +713,10 @@ class Generator(nn.Module):
         convolution (ST:802,806) and goes through PyTorch like the encoder's convolutions."""
         N.require_cuda(styles, input_noise)
         batch_size = styles.shape[0]
+        dd = bool(getattr(self, "double_backward", False))
         for block in self.blocks:      # the 3x3 convs follow the generator's precision (tensor cores in "bf16")
             block.conv1.precision = block.conv2.precision = self.precision
+            block.double_backward = block.to_rgb.double_backward = dd
         x = self.initial_conv(self.initial_block).expand(batch_size, -1, -1, -1)
         rgb = None
         coords = []

@@ -99,3 +99,10 @@ def selection_margin_report(eff_ref, base_ref, eff_other=None, base_other=None, 
         out["worst_image_err_over_mask_margin"] = float(worst["mask_ratio"])
         out["picks_provably_equal"] = bool(worst["ratio"] < 1 and worst["mask_ratio"] < 1 and out.get("label_flips", 0) == 0)
     return out
+
+
+def grad_digest(t, cap=4096):
+    """same as tests/golden/make_golden.py::grad_digest: strided sample of at most ``cap`` entries + (sum, sum |.|, sum .^2)."""
+    f = t.detach().reshape(-1).double().cpu()
+    step = max(1, (f.numel() + cap - 1) // cap)
+    return np.concatenate([[float(f.sum()), float(f.abs().sum()), float((f * f).sum())], f[::step].numpy()])
