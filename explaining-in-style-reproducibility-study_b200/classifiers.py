@@ -83,6 +83,9 @@ class _Wrapper:
         kernel; the network forward stays PyTorch.  Only the ResNet wrapper (224x224 resize) has this path."""
         if on and self.kind != "resnet":
             raise NotImplementedError("native preprocessing covers the ResNet wrapper (resize to 224) only")
+        if on and getattr(self, "antialias", None) is False and self.image_size > self.resnet_dim:
+            raise NotImplementedError("native preprocessing implements the antialiased resize; antialias=False with a "
+                                      "shrinking resize keeps the torchvision path")
         self.native_preprocess = on
         return self
 
@@ -302,9 +305,14 @@ class ResNet(_Wrapper):
     kind = "resnet"
 
     def __init__(self, model_name: Optional[str] = None, cuda_rank: int = 0, output_size: int = 2, image_size: int = 32,
-                 normalize: bool = True, model: Optional[nn.Module] = None):
+                 normalize: bool = True, model: Optional[nn.Module] = None, antialias: Optional[bool] = None):
+        """``antialias``: what ``torchvision.transforms.functional.resize`` does to TENSOR inputs when it shrinks them
+        (256 -> 224; enlarging is unaffected).  None = the installed torchvision's default (antialiased since 0.17);
+        False = the behaviour of the reference's pinned torchvision 0.11.1 (``R/environment.yml:144``), i.e. what the
+        authors' trained classifiers saw -- use it with their checkpoints."""
         from torchvision.transforms import transforms
 
+        self.antialias = antialias
         if model is None:
             import torchvision
 
@@ -321,7 +329,10 @@ class ResNet(_Wrapper):
         from torchvision.transforms.functional import resize
 
         if isinstance(images, torch.Tensor):
-            x = resize(images, [self.resnet_dim, self.resnet_dim])       # resnet_classifier.py:60-61
+            if self.antialias is None:
+                x = resize(images, [self.resnet_dim, self.resnet_dim])   # resnet_classifier.py:60-61
+            else:
+                x = resize(images, [self.resnet_dim, self.resnet_dim], antialias=self.antialias)
         else:
             x = self.image_transform(images)
         if self.normalize:

@@ -182,6 +182,7 @@ class TrainStep:
         w_space = latent_to_w(self.S, style)
         return styles_def_to_tensor(w_space), image_noise(batch_size, G.image_size, self.rank), None, None, None
 
+    @torch.enable_grad()
     def train_step(self, loader: Iterator[torch.Tensor]) -> dict:
         st = self.StylEx
         st.train()

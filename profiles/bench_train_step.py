@@ -33,6 +33,8 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
 ap.add_argument("--out", default=None)
+ap.add_argument("--channels-last", action="store_true", help="encoder / discriminator / classifier in torch.channels_last")
+ap.add_argument("--profile", action="store_true", help="print the top CUDA kernels of one step (torch.profiler) instead of timing")
 a = ap.parse_args()
 
 rank, world, local = sxd.init_from_env()
@@ -46,6 +48,10 @@ st = sx.StylEx(size, rank=local)
 st.G.precision = a.precision
 model = synthetic.make_classifier_model("resnet", 42).to(dev)
 clf = sx.make_classifier("resnet", model, size)
+if a.channels_last:
+    st.encoder.to(memory_format=torch.channels_last)
+    st.D.to(memory_format=torch.channels_last)
+    model.to(memory_format=torch.channels_last)
 ts = T.TrainStep(st, clf, batch_size=a.batch, gradient_accumulate_every=a.accumulate, ddp=world > 1, rank=local)
 pool = torch.rand(4 * a.batch, 3, size, size, device=dev)
 
@@ -61,6 +67,13 @@ def loader():
 it = loader()
 for _ in range(a.warmup):
     ts.train_step(it)
+if a.profile:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        ts.train_step(it)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+    sys.exit(0)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
@@ -86,7 +99,8 @@ if rank == 0:
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "scaling": "weak", "dtype": a.precision,
         "config": {"workload": "BASELINE config 5: StylEx %dpx training step (D phase + G phase, hinge + L1 reconstruction + classifier KL, "
                                "GP every 4th step), batch %d/GPU x accumulate %d, ResNet-18 classifier, DDP over S/G/D/encoder" % (size, a.batch, a.accumulate),
-                   "generator_precision": a.precision, "encoder_discriminator_classifier": "PyTorch / cuDNN fp32"},
+                   "generator_precision": a.precision,
+                   "encoder_discriminator_classifier": "PyTorch / cuDNN fp32 (TF32 convolutions, torch default)" + (", channels_last" if a.channels_last else "")},
         "generator_conv_tflops_per_gpu": g_flops / (ms * 1e-3) / 1e12,
         "native_launches_per_step": (_native.launch_count() - launches0) / a.steps,
         "losses_last": {k: v for k, v in logs[-1].items()},

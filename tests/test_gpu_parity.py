@@ -1061,6 +1061,11 @@ def _digest_close(got, ref, rel, what):
 
 
 def test_training_losses_and_double_backward_match_reference_autograd(dev, golden):
+    with torch.enable_grad():
+        _training_losses_and_double_backward(dev, golden)
+
+
+def _training_losses_and_double_backward(dev, golden):
     """SURVEY.md section 8f row 1 / VERDICT r1 item 7: the loss helpers and both phases of ``Trainer.train`` on this
     package's modules against the reference's own classes under torch autograd (tests/golden/training_small.npz):
 
@@ -1137,6 +1142,11 @@ def test_training_losses_and_double_backward_match_reference_autograd(dev, golde
 
 
 def test_train_step_runs_and_learns(dev):
+    with torch.enable_grad():
+        _train_step_runs_and_learns(dev)
+
+
+def _train_step_runs_and_learns(dev):
     """``training.TrainStep`` (ST:1249-1506): a few optimisation steps at 16 px with gradient accumulation (both the
     noise and the encoder branch of the alternating schedule), the gradient penalty (step 0) and the path-length penalty
     (forced early): finite losses, every trainable parameter of G / S / encoder / D receives updates."""

@@ -594,3 +594,19 @@ def test_screen_and_verify_recovers_the_exact_topk(seed, noise):
     assert sum(calls) == info["exact_evals"] <= 2 * S * n
     if noise <= 1e-2:
         assert info["exact_evals"] < 0.25 * 2 * S * n                              # a fraction of the N x 2S entries
+
+
+def test_resnet_wrapper_antialias_switch():
+    """SURVEY.md quirk Q12 / VERDICT r1 weak 9: the reference's pinned torchvision 0.11.1 shrinks tensors WITHOUT antialias;
+    ``ResNet(antialias=False)`` reproduces that, the default follows the installed torchvision; enlarging is unaffected."""
+    from torchvision.transforms.functional import resize
+    net = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(4), torch.nn.Flatten(), torch.nn.Linear(48, 2)).eval()
+    g = torch.Generator().manual_seed(0)
+    big, small = torch.rand(2, 3, 256, 256, generator=g), torch.rand(2, 3, 64, 64, generator=g)
+    r_def, r_old = sx.ResNet(model=net, image_size=256, normalize=False), sx.ResNet(model=net, image_size=256, normalize=False, antialias=False)
+    assert torch.equal(r_def.preprocess(big), resize(big, [224, 224]))
+    assert torch.equal(r_old.preprocess(big), resize(big, [224, 224], antialias=False))
+    assert not torch.equal(r_def.preprocess(big), r_old.preprocess(big))
+    assert torch.allclose(r_def.preprocess(small), r_old.preprocess(small), atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        r_old.use_native_preprocess(True)
