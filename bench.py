@@ -57,7 +57,9 @@ def parse():
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--classifier", default="resnet", choices=["resnet", "mobilenet"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--classifier-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--classifier-dtype", default=None, choices=["bf16", "fp32"],
+                    help="default: bf16 for the ResNet-18 wrapper, fp32 for MobileNetV2 (0.05 GFLOP per image, and its bf16 logits "
+                         "are off by ~1: profiles/README.md config 1)")
     ap.add_argument("--classifier-mode", default="fused", choices=["fused", "eager"],
                     help="fused: BatchNorm folded + PyTorch's fused cuDNN conv+bias+ReLU ops; eager: the module as is")
     ap.add_argument("--stem", default="s2d", choices=["s2d", "plain"],
@@ -375,6 +377,8 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False          # fp32 work (calibration, the parity-mode verification) is real fp32;
     torch.backends.cuda.matmul.allow_tf32 = False    # the bf16 throughput classifier is not affected
     size, kind = args.image_size, args.classifier
+    if args.classifier_dtype is None:
+        args.classifier_dtype = "bf16" if kind == "resnet" else "fp32"
     sd, model_cpu, noise_cpu = build_workload(size, kind)
     G = sx.Generator(size, 514).to(dev)
     G.load_state_dict(sd, strict=False)
@@ -577,7 +581,7 @@ def run_ours(args):
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": workload_name(size, S, kind) + f", {lps} latent(s)/rank/step x {S} coords x 2 directions",
                    "coord_evals_per_step": int(2 * S * lps * world), "max_batch": args.max_batch,
-                   "generator_dtype": args.precision, "classifier_dtype": args.classifier_dtype + " (PyTorch, channels_last)", "classifier_mode": clf_mode, "classifier_preprocess": pre_mode,
+                   "generator_dtype": args.precision, "classifier_dtype": info.get("dtype", args.classifier_dtype) + " (PyTorch, channels_last)", "classifier_mode": clf_mode, "classifier_preprocess": pre_mode,
                    "prefix_reuse": True, "l2": f"inputs larger than L2: every {args.max_batch}-eval batch streams >{args.max_batch * 16.8e6 / 1e9:.1f} GB of activations (L2 = 126 MB)",
                    "pool_latents": pool_n, "parallelism": f"latent-sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roofline, "cpu_baseline": cpu,

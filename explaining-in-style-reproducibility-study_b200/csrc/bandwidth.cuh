@@ -328,10 +328,14 @@ int launch_torgb(const T* y2, const float* rgb_style, int style_stride, const fl
   SX_REQUIRE((lpp & (lpp - 1)) == 0, "torgb: Co/%d = %d must be a power of two (or >= 32)", V, Co / V);
   SX_REQUIRE(Co / V < 32 || Co % (32 * V) == 0, "torgb: Co=%d must be a multiple of %d", Co, 32 * V);
   if (B == 0) return SX_OK;
-  const int TW = W < 16 ? W : 16, TH = H < 16 ? H : 16;
+  // 8 x 8 pixel tiles, 8 warps: a warp walks its pixels one after the other (load -> 48 FMAs -> shuffle reduce), so the
+  // loads in flight per SM are the number of resident warps.  With 16 x 16 tiles the 16 px / 512-channel launch was 256 CTAs
+  // of 32 serial pixels per warp: 835 GB/s (ncu r02b: 13 % of the copy bandwidth, latency-bound).  SX_TORGB_TILE=16: the old tiling.
+  static const int tile = getenv("SX_TORGB_TILE") ? atoi(getenv("SX_TORGB_TILE")) : 8;
+  const int TW = W < tile ? W : tile, TH = H < tile ? H : tile;
   SX_REQUIRE(W % TW == 0 && H % TH == 0, "torgb: H, W must be multiples of the tile");
   const int npix = TH * TW;
-  const int threads = npix >= 256 ? 256 : 128;   // >= 128: the 3*Co-entry weight table fill is a chain of dependent loads
+  const int threads = npix >= 64 ? 256 : 128;    // >= 128: the 3*Co-entry weight table fill is a chain of dependent loads
   dim3 grid((W / TW) * (H / TH), B);
   const size_t smem = (size_t)(3 * Co + 3 * 256 + 3 * (TH + 2) * (TW + 2)) * sizeof(float);
   torgb_kernel<T><<<grid, threads, smem, st>>>(y2, rgb_style, style_stride, wrgb, prev, prev_bstride, rgb, H, W, Co, TH, TW);

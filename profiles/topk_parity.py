@@ -82,7 +82,7 @@ def main():
     def classifier(mode):
         c = sx.make_classifier(kind, copy.deepcopy(model_cal).to(dev), size)
         if mode == "bench":
-            info = c.configure_throughput(calib[:8], dtype=torch.bfloat16)
+            info = c.configure_throughput(calib[:8], dtype=torch.bfloat16 if kind == "resnet" else torch.float32)
         else:   # the wrapper as the reference has it: eager fp32 module, torchvision resize + Normalize
             info = {"classifier_mode": "eager fp32 (TF32 off)", "preprocess": "torch (resize, Normalize)"}
         return c, info
