@@ -990,6 +990,7 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 4, 2, true, 4, 2, 2>(x, wk, p, stream);
   if (Co == 32 && bk == 32 && resident) {
     // column-parity form (SX_HALO_PAR bit 1): 4 stages of two 11 KB lattice boxes
+    if ((halo_par() & 8) && W >= 16) return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2, true>(x, wk, p, stream);   // 8 stages
     if ((halo_par() & 1) && W >= 16) return launch_conv_halo_cfg<32, 32, 4, 2, true, 4, 2, 2, true>(x, wk, p, stream);
     if (halo_variant() & 1) return launch_conv_halo_cfg<32, 32, 8, 2, true, 2, 2, 2>(x, wk, p, stream);
     return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2>(x, wk, p, stream);

@@ -610,3 +610,28 @@ def test_resnet_wrapper_antialias_switch():
     assert torch.allclose(r_def.preprocess(small), r_old.preprocess(small), atol=1e-6)
     with pytest.raises(NotImplementedError):
         r_old.use_native_preprocess(True)
+
+
+def test_configure_throughput_rejects_a_reduced_precision_network_that_moves_the_logits():
+    """classifiers.configure_throughput checks the bf16 network against the fp32 module on probe images first (measured need:
+    torchvision's MobileNetV2 in bf16 moved the logits of generated images by 1.2 of ~3); a network that fails keeps running
+    in fp32 with its ORIGINAL fp32 weights (the bf16 cast rounds them in place), and the description says so."""
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(3 * 8 * 8, 2)
+    with torch.no_grad():                       # large cancelling weights: fine in fp32, garbage in bf16
+        w = torch.randn(2, 96) * 300
+        lin.weight.copy_(torch.cat([w, -w * 1.003], dim=1))
+    net = torch.nn.Sequential(torch.nn.Flatten(), lin).eval()
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    c = sx.MobileNet(model=net, image_size=8, normalize=False)
+    half = torch.rand(4, 96) * 0.5 + 0.25
+    probe = torch.cat([half, half / 1.003], dim=1).reshape(4, 3, 8, 8)      # the two weight halves cancel on these inputs
+    ref = c.classify_images(probe)
+    info = c.configure_throughput(probe, dtype=torch.bfloat16)
+    assert info["dtype"] == "float32" and "rejected" in info["classifier_mode"], info
+    assert all(torch.equal(v, before[k]) for k, v in net.state_dict().items())
+    assert torch.allclose(c.classify_images(probe), ref, atol=1e-4)
+    # a well-conditioned network is accepted
+    net2 = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 2)).eval()
+    c2 = sx.MobileNet(model=net2, image_size=8, normalize=False)
+    assert c2.configure_throughput(probe, dtype=torch.bfloat16)["dtype"] == "bfloat16"
