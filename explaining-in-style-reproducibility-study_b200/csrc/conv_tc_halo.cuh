@@ -40,7 +40,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint3
 // is TMA-loaded (un-swizzled) into its own ring and the producer warps write the bilinearly upsampled 18 x 10 halo box
 // into the swizzled A stage (see the producer branch of the kernel).
 constexpr int UPS_SRC_W = HALO_W / 2 + 1, UPS_SRC_H = HALO_H / 2 + 1;   // 6 x 10 source pixels
-constexpr int UPS_S_STAGES = 2;
+constexpr int UPS_S_STAGES = 2;   // default depth of the low-resolution source-box ring (HaloCfg::kSrcStages)
 
 constexpr int halo_pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -83,7 +83,13 @@ struct HaloCfg {
   static constexpr int kThreads = kFrontThreads + kEpiThreads + kUpsThreads;
   static constexpr int kSrcW = PAR ? HALO_BW + 2 : UPS_SRC_W;           // low-res source columns: 10 for a 16-pixel super-tile
   static constexpr int kSrcBytes = kSrcW * UPS_SRC_H * kRowBytes;       // one source box (7680 B at BLOCK_K = 64; PAR: 12800 B)
-  static constexpr int kSrcRegion = UPS ? UPS_S_STAGES * kSrcBytes : 0;
+  // The source boxes are the fused-upsample layers' ONLY global loads: their ring depth is the memory-level parallelism of
+  // the CTA (2 boxes of 7.7 KB in flight per SM could not cover the DRAM latency; the plain 32->32 layer gained 18 % from
+  // 4 -> 8 stages, profiles/README.md r02).  Measured for the fused-upsample layers themselves (r02 r2o): 6 boxes instead of 2
+  // change nothing on 64->32 (0.852 ms either way: that layer is issue-bound), and trading weight-ring or resident-weight
+  // space for them makes 256->128 and 128->64 slower (0.562 -> 0.586, 0.591 -> 1.025 ms): 2 it stays.
+  static constexpr int kSrcStages = UPS_S_STAGES;
+  static constexpr int kSrcRegion = UPS ? kSrcStages * kSrcBytes : 0;
   static constexpr int kHaloW = PAR ? HALO_BW + 1 : HALO_W;             // pixel rows per halo row in a box (PAR: 9 per lattice)
   static constexpr int kBoxRows = kHaloW * HALO_H;
   static constexpr int kBoxBytes = (kBoxRows * kRowBytes + 1023) / 1024 * 1024;   // every box 1024 B aligned (swizzle phase)
@@ -94,7 +100,7 @@ struct HaloCfg {
   static constexpr int kTmemCols = halo_pow2_cols(SETS * kSlotCols);
   static_assert(SETS * kSlotCols <= 512, "TMEM has 512 columns");
   static constexpr int kBarBytes = 512;
-  static_assert((2 * A_STAGES + 2 * B_STAGES + 2 * SETS + 2 * UPS_S_STAGES) * 8 + 8 <= kBarBytes, "barrier block overflow");
+  static_assert((2 * A_STAGES + 2 * B_STAGES + 2 * SETS + 2 * kSrcStages) * 8 + 8 <= kBarBytes, "barrier block overflow");
   static constexpr int kTableFloats = (2 + 10 * SETS) * BLOCK_N;  // nw, nb, then per set 2 slots x (d, m, 3 rgb rows)
   __host__ __device__ static size_t b_region(int num_b_tiles) { return (size_t)(RESIDENT_B ? num_b_tiles : B_STAGES) * kBBytes; }
   static size_t smem_bytes(int num_b_tiles) {
@@ -150,6 +156,16 @@ __device__ __forceinline__ void epi_group4(const uint32_t* __restrict__ v, const
     float t0, t1, l0, l1;
     upk2(t2, t0, t1);
     upk2(l2, l0, l1);
+    if (RGB && !OUT && !RAW) {
+      // the last block: nothing stores this feature map (only its ToRGB sum leaves the kernel), so there is no storage type
+      // to round to -- the fp32 activation feeds the ToRGB accumulation directly (3 instructions fewer per channel pair,
+      // and closer to the fp32 reference).  Full and suffix forwards run this same kernel: still bit-identical to each other.
+      const uint64_t fr2 = pk2(fmaxf(t0, l0), fmaxf(t1, l1));
+      racc[0] = fma2(fr2, h ? pk2(t.r0.z, t.r0.w) : pk2(t.r0.x, t.r0.y), racc[0]);
+      racc[1] = fma2(fr2, h ? pk2(t.r1.z, t.r1.w) : pk2(t.r1.x, t.r1.y), racc[1]);
+      racc[2] = fma2(fr2, h ? pk2(t.r2.z, t.r2.w) : pk2(t.r2.x, t.r2.y), racc[2]);
+      continue;
+    }
     const uint32_t raw = bf16x2_rn(fmaxf(t0, l0), fmaxf(t1, l1));
     if (RAW) orw[h] = raw;
     if (OUT || RGB) {
@@ -197,8 +213,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = b_empty + B_STAGES;       // [SETS]
   uint64_t* tmem_empty = tmem_full + SETS;        // [SETS]
   uint64_t* s_full = tmem_empty + SETS;           // [UPS_S_STAGES]  (UPS only) source box landed
-  uint64_t* s_empty = s_full + UPS_S_STAGES;      // [UPS_S_STAGES]  (UPS only) producers are done with the source box
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_empty + UPS_S_STAGES);
+  uint64_t* s_empty = s_full + Cfg::kSrcStages;   // [kSrcStages]  (UPS only) producers are done with the source box
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_empty + Cfg::kSrcStages);
   float* s_nw = reinterpret_cast<float*>(after + Cfg::kBarBytes);
   float* s_nb = s_nw + BLOCK_N;
   float* s_tab = s_nb + BLOCK_N;          // [SETS][2 slots][d | m | rgb0 | rgb1 | rgb2][BLOCK_N]
@@ -241,7 +257,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], UPS ? Cfg::kUpsThreads : 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < SETS; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
-    if (UPS) for (int s = 0; s < UPS_S_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], Cfg::kUpsThreads); }
+    if (UPS) for (int s = 0; s < Cfg::kSrcStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], Cfg::kUpsThreads); }
     fence_barrier_init();
   } else if (warp_id == 1) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
@@ -288,7 +304,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_4d(smem_src + ss * Cfg::kSrcBytes, &tmap_a, &s_full[ss], chunk * BLOCK_K, x0 / 2 - 1, y0 / 2 - 1, b);
             }
             __syncwarp();
-            if (++ss == UPS_S_STAGES) { ss = 0; sph ^= 1; }
+            if (++ss == Cfg::kSrcStages) { ss = 0; sph ^= 1; }
           } else {
             const int st = rg * Cfg::kAHalf + as;
             mbar_wait(&a_empty[st], aph ^ 1, 10);
@@ -552,7 +568,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_arrive(&s_empty[ss]);
         if (pt == 0 && chunk == 0) SX_TRACE(7, tile - tile_begin);
         if (++as == Cfg::kAHalf) { as = 0; aph ^= 1; }
-        if (++ss == UPS_S_STAGES) { ss = 0; sph ^= 1; }
+        if (++ss == Cfg::kSrcStages) { ss = 0; sph ^= 1; }
       }
       if (rg) { as2[1] = as; aph2[1] = aph; } else { as2[0] = as; aph2[0] = aph; }
     }
@@ -957,7 +973,9 @@ inline ConvHaloParams make_halo_params(int B, int Ci, int Co, int H, int W, int 
 // SX_HALO_VARIANT (bitmask, tuning experiments): 1 = the 32 -> 32 layers run 2 epilogue sets (wide passes) instead of 4;
 // 2 = the 64 -> 64 layers run 2 sets x 2 tiles with two MMA warps instead of 4 sets x 1 tile with one;
 // 4 = the fused-upsample 128 -> 64 layer runs 2 tiles per slot with two MMA warps;
-// 8 = the weight-streaming Co = 128 layers run the old 4-deep weight ring instead of 8
+// 8 = the weight-streaming Co = 128 layers run the old 4-deep weight ring instead of 8.
+// Ring depths tried and rejected in round 2 (256 px, batch 256): plain 64 -> 64 with 6 activation stages 0.372 -> 0.390 ms,
+// plain 128 -> 128 with 4 activation stages + a 6-deep weight ring 0.282 -> 0.288 ms.
 // SX_HALO_MAX_CO: plain (non-upsample) layers wider than this go to conv_tc_kernel instead (A/B of the two kernels)
 // SX_HALO_PAR (bitmask, default 1): layers that run the column-parity form.  Measured at 256 px, batch 256 (profiles/README.md
 // r02d/e): 1 = 32 -> 32 (+ToRGB): 0.615 -> 0.551 ms (default ON); 2 = 64 -> 64 (+ToRGB) with 32-channel chunks x 4 stages:
@@ -989,9 +1007,10 @@ inline int launch_conv_halo(const __nv_bfloat16* x, const __nv_bfloat16* wk, int
   //                                                                    N   K  A  B  resident SETS TPS MMA-warps
   if (Co == 32 && bk == 64 && resident) return launch_conv_halo_cfg<32, 64, 4, 2, true, 4, 2, 2>(x, wk, p, stream);
   if (Co == 32 && bk == 32 && resident) {
-    // column-parity form (SX_HALO_PAR bit 1): 4 stages of two 11 KB lattice boxes
-    if ((halo_par() & 8) && W >= 16) return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2, true>(x, wk, p, stream);   // 8 stages
-    if ((halo_par() & 1) && W >= 16) return launch_conv_halo_cfg<32, 32, 4, 2, true, 4, 2, 2, true>(x, wk, p, stream);
+    // column-parity form (SX_HALO_PAR bit 1)
+    // 8 stages of two 11 KB lattice boxes (4 stages: 0.523 ms at 256 px / batch 256; 8: 0.445 -- the layer is load-latency bound)
+    if ((halo_par() & 8) && W >= 16) return launch_conv_halo_cfg<32, 32, 4, 2, true, 4, 2, 2, true>(x, wk, p, stream);   // A/B: 4 stages
+    if ((halo_par() & 1) && W >= 16) return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2, true>(x, wk, p, stream);
     if (halo_variant() & 1) return launch_conv_halo_cfg<32, 32, 8, 2, true, 2, 2, 2>(x, wk, p, stream);
     return launch_conv_halo_cfg<32, 32, 8, 2, true, 4, 2, 2>(x, wk, p, stream);
   }
