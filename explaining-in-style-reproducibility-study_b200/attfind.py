@@ -144,8 +144,9 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     effects = torch.zeros(hi - lo, 2, S, 2, device=dev, dtype=torch.float32)
     # coordinate runs per conv: [(conv index, first sindex, count)] -- contiguous runs of the requested sindices
     runs = _coord_runs(plan.conv_coords, sindices, half)
-    styles_b = torch.empty(max_batch, row, device=dev, dtype=torch.float32)
-    rgb_b = torch.empty(max_batch, 3, G.image_size, G.image_size, device=dev, dtype=torch.float32)
+    # per-plan scratch, kept across calls (bench.py sweeps one latent per call: 201 MB of rgb at batch 256 / 256 px)
+    styles_b = plan.scratch("sweep_styles", (max_batch, row), dev)
+    rgb_b = plan.scratch("sweep_rgb", (max_batch, 3, G.image_size, G.image_size), dev)
     evals = 0
     for n in mine:                                                                      # NB:346
         base_row = styles_all[n]

@@ -539,6 +539,7 @@ class GeneratorPlan:
         self._versions = None
         self._ws = {}            # precision -> Workspace
         self._cache_ok = {}      # precision -> bool (clean-prefix cache primed on the current workspace)
+        self._scratch = {}       # name -> tensor (scratch())
         pairs = [(b.input_channels, b.filters) for b in generator.blocks]
         self.pairs = pairs
         ci = (ctypes.c_int * len(pairs))(*[p[0] for p in pairs])
@@ -605,6 +606,14 @@ class GeneratorPlan:
         buf = ws.get(need, self.device)
         if buf.data_ptr() != old:
             self._cache_ok[prec] = False
+
+    def scratch(self, name: str, shape, device) -> torch.Tensor:
+        """a named fp32 scratch tensor owned by the plan, re-used across calls while shape and device stay the same"""
+        t = self._scratch.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != torch.device(device):
+            t = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+            self._scratch[name] = t
+        return t
 
     def styles(self, w: torch.Tensor) -> torch.Tensor:
         """w [B, L, latent] -> styles [B, row] = [style coords (S) | ToRGB styles]."""

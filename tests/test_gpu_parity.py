@@ -1182,3 +1182,85 @@ def _train_step_runs_and_learns(dev):
     moved = {n: float((p.detach() - before[n]).abs().max()) for n, p in st.named_parameters() if p.requires_grad}
     frozen = [n for n, v in moved.items() if v == 0.0 and not n.startswith(("SE.", "GE."))]
     assert not frozen, frozen
+
+
+def _small_tc_setup(dev, n, seed=11):
+    """32 px / capacity 16 generator (every conv tensor-core eligible) + a tiny conv classifier with O(1) logits"""
+    size, cap = 32, 16
+    sd = synthetic.make_generator_state(size, seed=seed, network_capacity=cap)
+    G = g_module(sd, size, cap, dev)
+    lat = synthetic.make_latents(n, seed).to(dev)
+    noise = synthetic.make_noise(size, seed).to(dev)
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, stride=2, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1),
+                                torch.nn.Flatten(), torch.nn.Linear(4, 2)).eval()
+    with torch.no_grad():
+        model[-1].weight.mul_(20)
+    clf = sx.make_classifier("mobilenet", model.to(dev), size)
+    G.precision = "fp32"
+    lg = clf.classify_images(G(sx.styles_def_to_tensor([(lat, G.num_layers)]).contiguous(), noise))
+    with torch.no_grad():                          # decision boundary between the base images: both classes populated
+        d = torch.sort(lg[:, 1] - lg[:, 0]).values
+        mid = float(d[(len(d) - 1) // 2] + d[(len(d) - 1) // 2 + 1]) / 2
+        model[-1].bias[1] -= mid / 2
+        model[-1].bias[0] += mid / 2
+    return G, clf, lat, noise
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sweep_edge_cases(dev, tc_ok, precision):
+    """Edge cases of the sweep (the reference has no tests; these follow from NB:340-387): ONE latent -- minima == maxima ==
+    its own coordinates, so every shift and therefore every effect is exactly 0, and the selection fails like the notebook
+    (one class is empty, quirk Q7); an EMPTY coordinate subset; an odd max_batch; a batch larger than the coordinate count."""
+    if precision == "bf16":
+        _need_tc(tc_ok)
+    G, clf, lat, noise = _small_tc_setup(dev, 3)
+    S = G.num_style_coords
+    one = sx.attfind_sweep(G, clf, lat[:1], noise, precision=precision, max_batch=64)
+    # the generator output is bit-identical to the base image (zero shift); the tiny classifier is one cuDNN convolution whose
+    # algorithm may depend on the batch size, hence a rounding-level bound instead of == 0 (the exact-zero property itself is
+    # test_sweep_properties_at_baseline_sizes, with a batch-size independent classifier)
+    assert one["style_change"].shape == (1, 2, S, 2) and float(one["style_change"].abs().max()) <= 1e-4
+    assert torch.equal(one["minima"], one["maxima"])
+    with pytest.raises(IndexError):
+        sx.attfind_select(one["style_change"], one["base_prob"], 5, 0.5)
+    none = sx.attfind_sweep(G, clf, lat, noise, precision=precision, sindices=[], max_batch=64)
+    assert float(none["style_change"].abs().max()) == 0.0
+    sind = list(range(100, 131)) + [S - 1]
+    a = sx.attfind_sweep(G, clf, lat, noise, precision=precision, sindices=sind, max_batch=7)      # odd: rounded down to 6
+    b = sx.attfind_sweep(G, clf, lat, noise, precision=precision, sindices=sind, max_batch=4096)   # one batch per conv
+    # our kernels are batch-size independent; the tiny classifier is one cuDNN conv whose algorithm may not be
+    assert float((a["style_change"] - b["style_change"]).abs().max()) <= 1e-4
+    mask = torch.ones(S, dtype=torch.bool)
+    mask[sind] = False
+    assert float(a["style_change"][:, :, mask].abs().max()) == 0.0
+
+
+def test_verify_topk_small_generator_equals_full_fp32_sweep(dev, tc_ok):
+    """attfind_verify_topk end to end on a small tensor-core generator, every coordinate: the picks and the merged list of
+    (bf16 sweep + verification) are those of the full fp32 sweep, and the oracle's selection on the hybrid effects agrees."""
+    _need_tc(tc_ok)
+    G, clf, lat, noise = _small_tc_setup(dev, 12, seed=13)
+    r32 = sx.attfind_sweep(G, clf, lat, noise, precision="fp32", max_batch=256)
+    want = sx.attfind_select(r32["style_change"], r32["base_prob"], 5, 0.5)
+    r16 = sx.attfind_sweep(G, clf, lat, noise, precision="bf16", max_batch=256)
+    picks, merged, scores, info = sx.attfind_verify_topk(G, clf, lat, noise, r16, 5, 0.5, precision="fp32", max_batch=64,
+                                                         min_candidates=8)
+    assert info["verified"]
+    assert picks == want[0] and merged == want[1]
+    ref = O.attfind_select(info["style_change"].cpu().numpy(), info["base_prob"].cpu().numpy(), 5, 0.5)
+    assert picks == ref[0] and merged == ref[1]
+    assert info["exact_evals"] < 0.6 * lat.shape[0] * 2 * G.num_style_coords
+
+
+def test_native_call_on_a_tensor_of_another_device_is_an_error(dev):
+    """launches go to the CURRENT device's stream; a tensor that lives elsewhere must raise, not fault."""
+    if torch.cuda.device_count() < 2:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            sx.modules.upsample2x(torch.zeros(1, 1, 2, 2))
+        return
+    other = torch.device("cuda", 1 if (dev.index or 0) == 0 else 0)
+    with pytest.raises(RuntimeError, match="current CUDA device"):
+        sx.modules.upsample2x(torch.zeros(1, 1, 2, 2, device=other))
+    with torch.cuda.device(other):
+        assert sx.modules.upsample2x(torch.ones(1, 1, 2, 2, device=other)).shape == (1, 1, 4, 4)
