@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--oracle-batch", type=int, default=128)
     ap.add_argument("--oracle-max-seconds", type=float, default=1200.0)
     ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--latent-seed", type=int, default=None, help="seed of the latents (default: --seed); 4242 = bench.py's job leg")
     ap.add_argument("--out", default=None)
     ap.add_argument("--dump", default=None, help="npz with the effects / base logits of the --dump-arms (float32)")
     ap.add_argument("--dump-arms", default="fp32,bench,bf16g_fp32c")
@@ -69,7 +70,7 @@ def main():
     G = sx.Generator(size, 514).to(dev)
     G.load_state_dict(sd, strict=False)
     L, S = G.num_layers, G.num_style_coords
-    lat = synthetic.make_latents(n, args.seed).to(dev)
+    lat = synthetic.make_latents(n, args.seed if args.latent_seed is None else args.latent_seed).to(dev)
 
     # calibration exactly like bench.py: fp32 generator images of 32 seeded latents
     clf0 = sx.make_classifier(kind, copy.deepcopy(model).to(dev), size)
