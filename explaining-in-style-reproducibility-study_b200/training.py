@@ -22,7 +22,6 @@ from typing import Callable, Iterator, Optional
 
 import torch
 import torch.nn.functional as F
-from torch import nn
 from torch.autograd import grad as torch_grad
 
 from .modules import image_noise, styles_def_to_tensor
