@@ -24,6 +24,19 @@ struct ConvSimtParams {
   ConvEpilogue ep;
 };
 
+// packed fp32x2 FMA (sm_100 FFMA2: two independent IEEE fmas per instruction -- same results as two fmaf)
+__device__ __forceinline__ uint64_t simt_pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void simt_upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t simt_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // Tile BM pixels x BN channels x 16, 256 threads, TM x TN register micro-tile.  Every output is the same sequential fp32
 // FMA chain over (tap, channel) whatever the tiling, so all configurations give bit-identical results:
 //   <128, 64, 8, 4>  large layers: 32 FMAs per 12 shared-memory floats (the 64 x 64 / 4 x 4 form: 16 per 8)
@@ -124,11 +137,14 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
     if (b_active) *reinterpret_cast<float4*>(&Bs[buf][b_kr][b_ng]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
   };
 
-  float acc[TM][TN];
+  // accumulators packed two rows per register pair: acc2[i2][j] = (row 2 i2, row 2 i2 + 1) of column j.  The row pairs come
+  // straight out of the float4 shared-memory loads; the TN column values are broadcast into both halves once per k.
+  // TM * TN / 2 FFMA2 + TN moves per k instead of TM * TN FFMA; per output element the same sequential fma chain.
+  uint64_t acc2[TM / 2][TN];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int i = 0; i < TM / 2; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc2[i][j] = 0ull;
 
   load_tiles(0);
   store_tiles(0);
@@ -138,24 +154,30 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvSimtParams 
     if (it + 1 < iters) load_tiles(it + 1);
 #pragma unroll
     for (int k = 0; k < SIMT_BK; ++k) {
-      float av[TM];
+      uint64_t pa[TM / 2];
 #pragma unroll
       for (int i4 = 0; i4 < TM / 4; ++i4) {
         const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4 * i4]);
-        av[4 * i4] = a.x; av[4 * i4 + 1] = a.y; av[4 * i4 + 2] = a.z; av[4 * i4 + 3] = a.w;
+        pa[2 * i4] = simt_pk2(a.x, a.y);
+        pa[2 * i4 + 1] = simt_pk2(a.z, a.w);
       }
       const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
-      const float bv[4] = {b.x, b.y, b.z, b.w};
+      const uint64_t bb[4] = {simt_pk2(b.x, b.x), simt_pk2(b.y, b.y), simt_pk2(b.z, b.z), simt_pk2(b.w, b.w)};
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+      for (int i = 0; i < TM / 2; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc2[i][j] = simt_fma2(pa[i], bb[j], acc2[i][j]);
     }
     if (it + 1 < iters) store_tiles(buf ^ 1);
     __syncthreads();
   }
 
   // ---- epilogue
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM / 2; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) simt_upk2(acc2[i][j], acc[2 * i][j], acc[2 * i + 1][j]);
   const ConvEpilogue& ep = p.ep;
   const int S = ep.noise_size;
 #pragma unroll
