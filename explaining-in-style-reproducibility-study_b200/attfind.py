@@ -310,7 +310,7 @@ def sharded_entries(evaluate, latent_idx: torch.Tensor, columns: torch.Tensor, r
 
 def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_entries, select, num_indices: int = 5,
                       effect_threshold: float = 0.5, min_candidates: int = 32, band_sigmas: float = 8.0,
-                      band_floor: float = 2.0, max_passes: int = 6):
+                      band_floor: float = 2.0, max_passes: int = 6, audit_columns: int = 8):
     """The selection logic of ``attfind_verify_topk`` (device-agnostic torch; see there).
 
     approx [N,2,S,2]: effects of the throughput-mode sweep; base_exact [N,2]: parity-mode base logits;
@@ -318,7 +318,11 @@ def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_entr
     pairs; ``select(effects, base_logits, k, effect_threshold) -> (picks, merged, scores)``: the exact selection
     (``attfind_select``).  Candidate columns of class c are re-evaluated for the images of class c only (the greedy
     selection of class c reads nothing else); the picked columns and their opposite directions, which the merged ranking
-    reads over ALL images (NB:806-809), are completed at the end.  Returns (picks, merged, scores, info)."""
+    reads over ALL images (NB:806-809), are completed at the end.  ``audit_columns`` (per class): once every round is
+    verified, that many RANDOM columns that were not candidates are re-evaluated too and their approximate-vs-exact
+    column-mean discrepancy is compared with the band -- the band was measured on the leaders only, this checks it on the
+    population it is applied to; a discrepancy above band / 2 doubles the band and the judgement is repeated
+    (``info['audit_max']``).  Returns (picks, merged, scores, info)."""
     n_all, _, S, _ = approx.shape
     dev = approx.device
     k = int(num_indices)
@@ -395,19 +399,43 @@ def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_entr
     _, need, _, _ = replay(collect_top=max(2, min_candidates))
     make_exact(need)
     picks_r = None
+    audited = audit_columns <= 0
+    band_min = 0.0
+    gen = torch.Generator().manual_seed(20211)            # the same audit columns on every rank
     for p in range(max_passes):
         info["passes"] = p + 1
         # the band from the measured discrepancy of the candidates' masked column means
         _, _, _, disc = replay()
         d = torch.cat(disc)
-        band = max(band_sigmas * float(d.std()), band_floor * float(d.abs().max()))
+        band = max(band_sigmas * float(d.std()), band_floor * float(d.abs().max()), band_min)
         info.update(band=band, colmean_err_std=float(d.std()), colmean_err_max=float(d.abs().max()))
         ok, need, picks_r, _ = replay(band=band)
-        if ok:
+        if not ok:
+            make_exact(need)
+            continue
+        if audited:
             info["verified"] = True
             break
-        # add the violators plus everything within a further band of them, so that a second pass is rarely needed
-        make_exact(need)
+        # audit: the band on a random sample of the columns it was applied to without being measured on them
+        audited = True
+        worst = 0.0
+        extra = {}
+        for c in (0, 1):
+            free = (~is_exact[c]).nonzero().flatten().cpu()
+            if free.numel() == 0:
+                continue
+            pick = free[torch.randperm(free.numel(), generator=gen)[:audit_columns]]
+            extra[c] = pick.tolist()
+        make_exact(extra)
+        for c, cols in extra.items():
+            idx = torch.tensor(cols, device=dev, dtype=torch.long)
+            exact_cm = hybrid[rows[c]][:, :, :, c].reshape(rows[c].numel(), 2 * S)[:, idx].double().clamp_(min=0).mean(dim=0)
+            worst = max(worst, float((E_apx[c][:, idx].mean(dim=0) - exact_cm).abs().max()))
+        info["audit_max"] = worst
+        if worst <= band / 2:
+            info["verified"] = True
+            break
+        band_min = 2 * worst                              # the leaders under-estimated the error: widen and judge again
     # the merged ranking (NB:806-809) reads both directions of every picked coordinate over ALL images
     both = [x for c in (0, 1) for x in picks_r[c]]
     both += [(1 - x // S) * S + x % S for x in both]
@@ -426,7 +454,7 @@ def screen_and_verify(approx: torch.Tensor, base_exact: torch.Tensor, exact_entr
 def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: torch.Tensor, sweep: Dict[str, torch.Tensor],
                         num_indices: int = 5, effect_threshold: float = 0.5, shift_size: float = 1.0, precision: str = "fp32",
                         max_batch: int = 128, rank: int = 0, world_size: int = 1, min_candidates: int = 32,
-                        band_sigmas: float = 8.0, band_floor: float = 2.0, max_passes: int = 6):
+                        band_sigmas: float = 8.0, band_floor: float = 2.0, max_passes: int = 6, audit_columns: int = 8):
     """The reference's EXACT top-k (NB:731-814) out of a throughput-mode sweep: screen in bf16, verify in fp32.
 
     A bf16 generator + bf16 classifier moves every effect by ~1e-2 of its size; the greedy selection of NB:751-756 is an
@@ -445,7 +473,8 @@ def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: 
        ``band = max(band_sigmas * std(d), band_floor * max|d|)``;
     5. replays the selection on the hybrid effects: a round is VERIFIED when its winner is an exact column and no
        non-candidate column comes within ``band`` of it (its true mean then cannot exceed the winner's).  Columns that do
-       are added to the candidates and steps 3-5 repeat (``max_passes``);
+       are added to the candidates and steps 3-5 repeat (``max_passes``); once every round passes, ``audit_columns`` random
+       non-candidate columns per class are re-evaluated as well and the band is checked (and widened if need be) on them;
     6. the picked columns and their opposite directions (the merged ranking reads them over ALL images, NB:806-809) are
        completed, and the final picks / merged list come from ``attfind_select`` (numpy-exact float64 kernels) on the
        hybrid effects.
@@ -491,7 +520,7 @@ def attfind_verify_topk(G: Generator, classifier, latents: torch.Tensor, noise: 
             latent_idx, columns, rank, world_size)
 
     return screen_and_verify(approx, base_exact, exact_entries, attfind_select, num_indices, effect_threshold,
-                             min_candidates, band_sigmas, band_floor, max_passes)
+                             min_candidates, band_sigmas, band_floor, max_passes, audit_columns)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -592,6 +592,7 @@ def test_screen_and_verify_recovers_the_exact_topk(seed, noise):
     assert picks == want[0] and merged == want[1]
     assert scores == want[2]
     assert sum(calls) == info["exact_evals"] <= 2 * S * n
+    assert info["audit_max"] <= info["band"] / 2                                   # the random-column audit confirms the band
     if noise <= 1e-2:
         assert info["exact_evals"] < 0.25 * 2 * S * n                              # a fraction of the N x 2S entries
 
