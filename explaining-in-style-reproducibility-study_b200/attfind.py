@@ -534,13 +534,18 @@ DATASET_NAMES = ("style_change", "latents", "base_prob", "minima", "maxima", "st
 def attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, dataset_name, noise, num_style_coords,
                        shift_size, discriminator_threshold, image_size=64, batch_size=1, cuda_rank=0,
                        use_discriminator=False, use_old_architecture=True, precision=None, max_batch=128,
-                       rank=0, world_size=1, front_batch=256):
+                       rank=0, world_size=1, front_batch=256, verify_classifier=None, num_indices=5, effect_threshold=0.5):
     """``attfind_extraction`` of NB:269-417 with the same arguments (extra keyword arguments have defaults).
 
     Phase A (encode each image, classify it, build ``concat_w``, discriminator output and optional filter;
     NB:300-336) runs batched through ``stylex.encode_images`` (``front_batch`` images per launch; the dataloader
     still yields one image per item, NB:284-285); phases B-C are ``attfind_sweep``.  Writes ``style_change_records.hdf5`` with the 9 datasets of NB:395-403 (h5py when importable, else
     the built-in minimal writer); also returns them as a dict.
+
+    ``verify_classifier`` (a parity-mode wrapper: fp32, eager): when the sweep ran in a reduced precision, the top-k
+    candidates are re-evaluated in fp32 (``attfind_verify_topk``) and the records carry the HYBRID effects + exact base
+    logits, so that the notebook's selection cells 14-16 (``find_significant_styles`` on the loaded records) return the
+    picks of a full fp32 sweep; the returned dict then also has 'picks', 'merged' and 'verify'.
     """
     if batch_size != 1:
         raise ValueError('Please use a batch_size equal to 1')                          # NB:284-285
@@ -548,12 +553,13 @@ def attfind_extraction(dataloader, num_images, results_folder, stylex, classifie
     with torch.cuda.device(dev):      # native launches go to the CURRENT device's stream: make cuda_rank current
         return _attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, noise, num_style_coords,
                                    shift_size, discriminator_threshold, image_size, dev, use_discriminator,
-                                   use_old_architecture, precision, max_batch, rank, world_size, front_batch)
+                                   use_old_architecture, precision, max_batch, rank, world_size, front_batch,
+                                   verify_classifier, num_indices, effect_threshold)
 
 
 def _attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, noise, num_style_coords, shift_size,
                         discriminator_threshold, image_size, dev, use_discriminator, use_old_architecture, precision,
-                        max_batch, rank, world_size, front_batch):
+                        max_batch, rank, world_size, front_batch, verify_classifier=None, num_indices=5, effect_threshold=0.5):
     G = stylex.G
     if num_style_coords != G.num_style_coords:
         raise ValueError(f"num_style_coords={num_style_coords} but the generator has {G.num_style_coords} (quirk Q5)")
@@ -600,6 +606,13 @@ def _attfind_extraction(dataloader, num_images, results_folder, stylex, classifi
     # fewer images than asked for: the notebook's unfilled (zero) rows take part in its min / max (NB:291, 340)
     res = attfind_sweep(G, classifier, image_latents[:images_found], noise, shift_size=shift_size, precision=precision,
                         max_batch=max_batch, rank=rank, world_size=world_size, zero_row=images_found < num_images)
+    extra = {}
+    if verify_classifier is not None:
+        picks, merged, scores, info = attfind_verify_topk(G, verify_classifier, image_latents[:images_found], noise, res,
+                                                          num_indices, effect_threshold, shift_size=shift_size, precision="fp32",
+                                                          max_batch=max_batch, rank=rank, world_size=world_size)
+        res = dict(res, style_change=info["style_change"], base_prob=info["base_prob"])
+        extra = {"picks": picks, "merged": merged, "verify": {k: v for k, v in info.items() if k not in ("style_change", "base_prob")}}
     out = {
         "style_change": _pad(res["style_change"], num_images), "latents": image_latents,
         "base_prob": _pad(res["base_prob"], num_images), "minima": res["minima"][None], "maxima": res["maxima"][None],
@@ -608,6 +621,7 @@ def _attfind_extraction(dataloader, num_images, results_folder, stylex, classifi
     }
     if rank == 0 and results_folder is not None:
         save_records(results_folder, out)
+    out.update(extra)
     return out
 
 

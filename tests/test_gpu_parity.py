@@ -1264,3 +1264,42 @@ def test_native_call_on_a_tensor_of_another_device_is_an_error(dev):
         sx.modules.upsample2x(torch.zeros(1, 1, 2, 2, device=other))
     with torch.cuda.device(other):
         assert sx.modules.upsample2x(torch.ones(1, 1, 2, 2, device=other)).shape == (1, 1, 4, 4)
+
+
+def test_attfind_extraction_with_verification_writes_records_that_select_like_fp32(dev, tc_ok, tmp_path):
+    """the notebook-signature entry point in the throughput mode + ``verify_classifier``: the records it writes carry the hybrid
+    effects, and the notebook's own selection on the LOADED records (cells 12, 14-16: ``load_records`` -> class split ->
+    ``find_significant_styles`` per class) returns the picks of the same extraction run entirely in fp32."""
+    _need_tc(tc_ok)
+    G, clf, _, noise = _small_tc_setup(dev, 4, seed=17)
+    size = G.image_size
+
+    class Enc(torch.nn.Module):
+        def forward(self, img):
+            f = torch.nn.functional.adaptive_avg_pool2d(img, 16).reshape(img.shape[0], -1)[:, :512]
+            return ((f - 0.5) * 6).squeeze()
+
+    class Stylex:
+        pass
+
+    st = Stylex()
+    st.G, st.encoder, st.D = G, Enc(), None
+    g = torch.Generator().manual_seed(5)
+    images = [torch.rand(1, 3, size, size, generator=g) for _ in range(12)]
+    S = G.num_style_coords
+    G.precision = "fp32"
+    ref = sx.attfind_extraction(images, 12, None, st, clf, None, noise, S, 1.0, -0.5, image_size=size, precision="fp32", max_batch=128)
+    labels = torch.argmax(ref["base_prob"], dim=1)
+    if int((labels == 0).sum()) in (0, 12):
+        pytest.skip("degenerate class split for this seed")
+    want = sx.attfind_select(ref["style_change"], ref["base_prob"], 5, 0.5)
+    out = sx.attfind_extraction(images, 12, str(tmp_path), st, clf, None, noise, S, 1.0, -0.5, image_size=size, precision="bf16",
+                                max_batch=128, verify_classifier=clf)
+    assert out["verify"]["verified"] and out["picks"] == want[0] and out["merged"] == want[1]
+    rec = sx.load_records(os.path.join(str(tmp_path), "style_change_records.hdf5"))
+    eff, base = rec["style_change"], rec["base_prob"]
+    lab = np.argmax(base, axis=1)
+    for c in (0, 1):                                                     # cells 14-16 on the loaded arrays
+        per_class = eff[lab == c].astype(np.float64)
+        got = sx.find_significant_styles(per_class, 5, c, max_image_effect=2.5, device=dev)
+        assert got == want[0][c], (c, got, want[0][c])
