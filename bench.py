@@ -62,8 +62,9 @@ def parse():
                          "are off by ~1: profiles/README.md config 1)")
     ap.add_argument("--classifier-mode", default="fused", choices=["fused", "eager"],
                     help="fused: BatchNorm folded + PyTorch's fused cuDNN conv+bias+ReLU ops; eager: the module as is")
-    ap.add_argument("--stem", default="s2d", choices=["s2d", "plain"],
-                    help="fused classifier stem: the 7x7/stride-2 conv re-expressed as a 4x4/stride-1 conv on the space-to-depth input, or as is")
+    ap.add_argument("--stem", default="native", choices=["native", "s2d", "plain"],
+                    help="fused classifier stem: the 7x7/stride-2 conv re-expressed as a 4x4/stride-1 conv on the space-to-depth input "
+                         "(native: in the tcgen05 kernel sx_stem_s2d_conv_relu, with the max-pool fused; s2d: through cuDNN), or as is")
     ap.add_argument("--maxpool", default="native", choices=["native", "torch"],
                     help="fused classifier stem max-pool: sx_maxpool3x3s2_nhwc (bit-identical) or F.max_pool2d")
     ap.add_argument("--preprocess", default="native", choices=["native", "torch"],

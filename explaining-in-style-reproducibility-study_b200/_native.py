@@ -61,6 +61,7 @@ SIGNATURES = {
     "sx_resize_aa_normalize_s2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),
                                            POINTER(c_float), c_void_p]),
     "sx_maxpool3x3s2_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sx_stem_s2d_conv_relu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sx_generator_create": (c_int, [POINTER(c_int), POINTER(c_int), c_int, c_int, POINTER(c_void_p)]),
     "sx_generator_destroy": (None, [c_void_p]),
     "sx_generator_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(sx_block_params), c_void_p]),
@@ -114,8 +115,8 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.sx_version() != 101:
-            raise RuntimeError(f"{LIB_PATH}: version {l.sx_version()} does not match the Python binding (101); rebuild")
+        if l.sx_version() != 102:
+            raise RuntimeError(f"{LIB_PATH}: version {l.sx_version()} does not match the Python binding (102); rebuild")
         _lib = l
     return _lib
 

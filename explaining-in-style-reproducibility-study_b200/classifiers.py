@@ -90,13 +90,14 @@ class _Wrapper:
         return self
 
     def configure_throughput(self, probe: torch.Tensor, dtype: torch.dtype = torch.bfloat16, fused: bool = True,
-                             stem: str = "s2d", maxpool: str = "native", preprocess: str = "native",
+                             stem: str = "native", maxpool: str = "native", preprocess: str = "native",
                              tol_rel: float = 0.05, tol_abs: float = 0.05):
         """The AttFind throughput configuration of the PyTorch classifier (what ``bench.py`` measures), in one place:
         ``dtype`` + channels_last, then -- each validated on ``probe`` (real generated images) against the logits of the
         module as it stood before the switch, and rolled back when it deviates by more than ``tol_rel * max|logit| +
-        tol_abs`` -- BatchNorm folding + fused cuDNN conv ops, the space-to-depth stem, the native max-pool and the
-        native one-pass preprocessing.  fp32 turns TF32 off (parity mode).  Returns {"classifier_mode", "preprocess"}
+        tol_abs`` -- BatchNorm folding + fused cuDNN conv ops, the space-to-depth stem (``stem="s2d"``: through cuDNN;
+        ``"native"``: bf16 only, the tcgen05 kernel ``sx_stem_s2d_conv_relu`` with the max-pool fused when ``maxpool`` is
+        "native"), the native max-pool and the native one-pass preprocessing.  fp32 turns TF32 off (parity mode).  Returns {"classifier_mode", "preprocess"}
         describing what is active."""
         def deviates(ref, got, scale=1.0):
             tol = scale * (tol_rel * float(ref.abs().max()) + tol_abs)
@@ -127,16 +128,28 @@ class _Wrapper:
             try:
                 ref = self.classify_images(probe)
                 self.fuse_for_inference()
-                if stem == "s2d":
+                if stem in ("s2d", "native"):
                     self.fused.enable_s2d_stem()
                 if maxpool == "native":
                     self.fused.enable_native_pool()
                 bad, err, tol = deviates(ref, self.classify_images(probe))
                 if bad:
                     raise RuntimeError(f"fused classifier deviates: {err:.3e} > {tol:.3e}")
-                mode = ("fused (BN folded, aten::cudnn_convolution_[add_]relu"
-                        + (", 7x7/2 stem as 4x4/1 on space-to-depth input" if stem == "s2d" else "")
-                        + (", native 3x3/2 max-pool)" if maxpool == "native" else ")"))
+                stem_note = ", 7x7/2 stem as 4x4/1 on space-to-depth input" if stem in ("s2d", "native") else ""
+                pool_note = ", native 3x3/2 max-pool)" if maxpool == "native" else ")"
+                if stem == "native" and dtype == torch.bfloat16:
+                    try:
+                        self.fused.enable_native_stem(fuse_pool=(maxpool == "native"))
+                        bad, err, tol = deviates(ref, self.classify_images(probe))
+                        if bad:
+                            raise RuntimeError(f"deviates: {err:.3e} > {tol:.3e}")
+                        stem_note += " in the native tcgen05 kernel sx_stem_s2d_conv_relu"
+                        if maxpool == "native":
+                            pool_note = ", 3x3/2 max-pool fused into the stem kernel)"
+                    except Exception as e:  # noqa: BLE001 -- keep the validated cuDNN stem, and say so
+                        self.fused.native_stem = None
+                        stem_note += f" (native stem kernel unavailable: {type(e).__name__}: {str(e)[:80]})"
+                mode = "fused (BN folded, aten::cudnn_convolution_[add_]relu" + stem_note + pool_note
             except Exception as e:  # noqa: BLE001 -- any failure means: keep the eager module, and say so
                 self.fused = None
                 mode = f"eager (fused path unavailable: {type(e).__name__}: {str(e)[:120]})"
@@ -225,6 +238,38 @@ class FusedResNetInference:
         self.fc_b = model.fc.bias.detach().to(dtype)
         self.stem_s2d = None
         self.native_pool = False
+        self.native_stem = None
+
+    def enable_native_stem(self, fuse_pool: bool = True):
+        """Opt-in (bf16, 64 stem channels, after ``enable_s2d_stem``): conv1 + bn1 + relu -- and with ``fuse_pool`` the
+        max-pool behind it -- run as ``sx_stem_s2d_conv_relu``, one tcgen05 kernel on the space-to-depth input (cuDNN has no
+        efficient tile for K = 16 per tap: its kernel and the separate pool were 10 % of the AttFind step).  Same values as
+        ``cudnn_convolution_relu`` + ``max_pool2d`` up to the order of the fp32 accumulation."""
+        if self.stem_s2d is None:
+            raise RuntimeError("enable_native_stem: call enable_s2d_stem first")
+        w, b = self.stem_s2d
+        if self.dtype != torch.bfloat16 or tuple(w.shape) != (64, 16, 4, 4) or not w.is_cuda:
+            raise TypeError("native stem: bf16 CUDA weights of shape [64,16,4,4] expected")
+        taps = w.permute(2, 3, 0, 1).contiguous()                      # [ky, kx, co, ci]
+        self.native_stem = (taps, b.float().contiguous(), bool(fuse_pool))
+        return self
+
+    def _stem_native(self, x: torch.Tensor) -> torch.Tensor:
+        from . import _native as N
+
+        taps, bias, fuse_pool = self.native_stem
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 16
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            raise TypeError("native stem: channels_last bf16 [B,16,H,W] space-to-depth input expected")
+        N.require_cuda(x, taps, bias)
+        b, _, h, w = x.shape
+        ho, wo = h - 3, w - 3
+        if fuse_pool:
+            ho, wo = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+        out = torch.empty((b, 64, ho, wo), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        N.check(N.lib().sx_stem_s2d_conv_relu(x.data_ptr(), taps.data_ptr(), bias.data_ptr(), out.data_ptr(), b, h, w,
+                                              1 if fuse_pool else 0, N.stream_ptr()), "sx_stem_s2d_conv_relu")
+        return out
 
     def enable_native_pool(self, on: bool = True):
         """Opt-in: the 3x3 / stride-2 / pad-1 max-pool after the stem runs as sx_maxpool3x3s2_nhwc (bit-identical to
@@ -261,6 +306,8 @@ class FusedResNetInference:
         if self.stem_s2d is not None:
             if not s2d_input:
                 x = space_to_depth_input(x)
+            if self.native_stem is not None:
+                return self._trunk(self._stem_native(x), pooled=self.native_stem[2])
             x = torch.cudnn_convolution_relu(x, self.stem_s2d[0], self.stem_s2d[1], (1, 1), (0, 0), (1, 1), 1)
         else:
             w, b, s, p = self.stem
@@ -276,8 +323,9 @@ class FusedResNetInference:
         w = (w * scale[:, None, None, None]).to(self.dtype).contiguous(memory_format=torch.channels_last)
         return w, b.to(self.dtype), tuple(conv.stride), tuple(conv.padding)
 
-    def _trunk(self, x: torch.Tensor) -> torch.Tensor:
-        x = self._pool(x)
+    def _trunk(self, x: torch.Tensor, pooled: bool = False) -> torch.Tensor:
+        if not pooled:
+            x = self._pool(x)
         for (w1, b1, s1, p1), (w2, b2, s2, p2), ds in self.blocks:
             identity = x if ds is None else F.conv2d(x, ds[0], ds[1], ds[2], ds[3])
             out = torch.cudnn_convolution_relu(x, w1, b1, s1, p1, (1, 1), 1)

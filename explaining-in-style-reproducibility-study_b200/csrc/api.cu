@@ -13,6 +13,7 @@
 #include "conv_tc_halo.cuh"
 #include "generator.cuh"
 #include "preprocess.cuh"
+#include "stem_tc.cuh"
 #include "wgrad_tc.cuh"
 
 using namespace sx;
@@ -434,6 +435,17 @@ int sx_maxpool3x3s2_nhwc(const void* in, void* out, int is_bf16, int B, int H, i
   if (is_bf16)
     return launch_maxpool3x3s2_nhwc<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, S(stream));
   return launch_maxpool3x3s2_nhwc<float>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), B, H, W, C, S(stream));
+}
+
+int sx_stem_s2d_conv_relu(const void* x, const void* w_taps, const float* bias, void* out, int B, int Hin, int Win, int fuse_pool,
+                          sx_stream_t stream) {
+  SX_REQUIRE(B >= 0 && Hin >= 4 && Win >= 4, "bad shape");
+  if (B == 0) return SX_OK;
+  SX_REQUIRE(x && w_taps && bias && out, "null argument");
+  SX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_taps) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem: 16-byte aligned buffers required");
+  return tc::launch_stem_s2d(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w_taps), bias,
+                             reinterpret_cast<__nv_bfloat16*>(out), B, Hin, Win, fuse_pool, S(stream));
 }
 
 // -------------------------------------------------------------------------------------------------

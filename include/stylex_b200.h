@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SX_VERSION 101
+#define SX_VERSION 102
 
 #define SX_OK 0
 #define SX_EINVAL (-1)       /* bad argument */
@@ -146,6 +146,15 @@ int sx_resize_aa_normalize_s2d(const float* in, void* out, int out_bf16, int B, 
  * resnet.py `self.maxpool`, reached from resnet_classifier.py:71) -- bit-identical to ATen's kernel, NaNs propagate.
  * C must be a multiple of 8 (bf16) / 4 (fp32). */
 int sx_maxpool3x3s2_nhwc(const void* in, void* out, int is_bf16, int B, int H, int W, int C, sx_stream_t stream);
+
+/* The ResNet stem of the classifier wrapper (resnet_classifier.py:56-71 -> torchvision resnet.py conv1 + bn1 + relu, and
+ * with fuse_pool the 3x3/2/1 maxpool after it) as one tcgen05 kernel on the space-to-depth input that
+ * sx_resize_aa_normalize_s2d writes.  x: bf16 [B, Hin, Win, 16]; w_taps: bf16 [4][4][64][16] = the BatchNorm-folded 7x7
+ * stride-2 weights re-indexed as 4x4 stride-1 taps (ky, kx, co, ci); bias: fp32 [64]; out: bf16 NHWC
+ * [B, Hin-3, Win-3, 64], or with fuse_pool [B, (Hin-4)/2+1, (Win-4)/2+1, 64].  Values: relu(conv + bias) accumulated in
+ * fp32 and rounded to bf16 once (what cudnn_convolution_relu stores), then the max. */
+int sx_stem_s2d_conv_relu(const void* x, const void* w_taps, const float* bias, void* out, int B, int Hin, int Win, int fuse_pool,
+                          sx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Generator plan -- sits under Generator.forward (ST:794-825) and the notebook's repeated

@@ -1303,3 +1303,57 @@ def test_attfind_extraction_with_verification_writes_records_that_select_like_fp
         per_class = eff[lab == c].astype(np.float64)
         got = sx.find_significant_styles(per_class, 5, c, max_image_effect=2.5, device=dev)
         assert got == want[0][c], (c, got, want[0][c])
+
+
+@pytest.mark.parametrize("fuse_pool", [False, True])
+@pytest.mark.parametrize("shape", [(3, 115, 115), (2, 23, 30), (1, 4, 4), (5, 35, 19), (0, 8, 8)])
+def test_native_stem_kernel_matches_conv_relu_pool(dev, tc_ok, shape, fuse_pool):
+    """sx_stem_s2d_conv_relu (tcgen05, 4x4 taps on the 16-channel space-to-depth input, SWIZZLE_32B halo boxes) against
+    relu(conv2d + bias) in fp32 on the same bf16 operands, rounded to bf16 once, then max_pool2d: equal up to the order of
+    the fp32 accumulation (<= 1 bf16 ulp on a few elements), ragged sizes and the pool's borders included."""
+    _need_tc(tc_ok)
+    from stylex_b200.classifiers import FusedResNetInference
+    b, h, w = shape
+    g = torch.Generator().manual_seed(h * 131 + w)
+    x = torch.randn(b, 16, h, w, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(64, 16, 4, 4, generator=g) * 0.1).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(64, generator=g).to(dev).to(torch.bfloat16)
+    f = FusedResNetInference.__new__(FusedResNetInference)
+    f.dtype, f.stem_s2d, f.native_stem = torch.bfloat16, (wt, bias), None
+    f.enable_native_stem(fuse_pool=fuse_pool)
+    got = f._stem_native(x)
+    ref = torch.relu(torch.nn.functional.conv2d(x.float(), wt.float(), bias.float())).to(torch.bfloat16)
+    if fuse_pool:
+        ref = torch.nn.functional.max_pool2d(ref, 3, 2, 1)
+    assert got.shape == ref.shape and got.dtype == torch.bfloat16
+    if b == 0:
+        return
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    diff = (got.float() - ref.float()).abs()
+    assert float(diff.max()) <= 2.0 ** -7 * max(1.0, float(ref.float().abs().max())), float(diff.max())
+    assert float((diff > 0).float().mean()) < 0.02
+
+
+def test_native_stem_in_the_classifier(dev, tc_ok):
+    """configure_throughput's default (bf16, native stem with the pool fused) stays within the reduced-precision tolerance
+    of the fp32 module, reports the native stem as active, and matches the cuDNN s2d stem it replaces far more closely."""
+    _need_tc(tc_ok)
+    model = synthetic.make_classifier_model("resnet", 5)
+    g = torch.Generator().manual_seed(1)
+    imgs = (torch.rand(6, 3, 256, 256, generator=g) * 2 - 0.5)
+    clf = sx.make_classifier("resnet", model, 256)
+    synthetic.calibrate_classifier(model, clf.preprocess, imgs, chunk=6)
+    clf.to(dev)
+    x = imgs.to(dev)
+    ref32 = clf.classify_images(x).float()
+    info = clf.configure_throughput(x)
+    assert "sx_stem_s2d_conv_relu" in info["classifier_mode"] and "fused into the stem" in info["classifier_mode"], info
+    assert clf.fused.native_stem is not None
+    got = clf.classify_images(x).float()
+    # bf16 network vs the fp32 module: the bound configure_throughput itself accepts a reduced-precision network under
+    assert float((got - ref32).abs().max()) <= 3 * (0.05 * float(ref32.abs().max()) + 0.05)
+    stem = clf.fused.native_stem
+    clf.fused.native_stem = None
+    cudnn = clf.classify_images(x).float()
+    clf.fused.native_stem = stem
+    assert float((got - cudnn).abs().max()) <= 2e-2 * max(1.0, float(ref32.abs().max()))

@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/stylex_b200.h but not exported"
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
-    assert lib.sx_version() == 101
+    assert lib.sx_version() == 102
     assert lib.sx_generator_workspace_bytes(None, 1, 0) == 0
 
 
