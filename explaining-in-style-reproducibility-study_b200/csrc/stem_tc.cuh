@@ -38,6 +38,8 @@ struct StemParams {
   int B, Hout, Wout;            // conv output
   int Ho, Wo;                   // what is stored: the conv output, or (POOL) the pooled map
   int tiles_x, tiles_y, num_tiles;
+  int debug;                    // SX_STEM_DEBUG bitmask (bottleneck experiments; results are garbage when set):
+                                //   1 skip epilogue math / stores, 2 skip MMA issue, 4 skip the activation TMA loads
   const float* bias;
   __nv_bfloat16* out;           // NHWC [B, Ho, Wo, 64]
 };
@@ -59,6 +61,14 @@ __device__ __forceinline__ uint64_t make_smem_desc32(uint32_t smem_addr, uint32_
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// packed fp32x2 -> bf16x2 (round to nearest even) with negative values clamped to +0
+__device__ __forceinline__ uint32_t relu_bf16x2_rn(uint64_t v2) {
+  float lo, hi;
+  upk2(v2, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -126,8 +136,12 @@ stem_s2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int half = 0; half < 2; ++half) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 0);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], STEM_BOX_BYTES);
-          tma_load_4d(smem_a + stage * STEM_STAGE_BYTES, &tmap_a, &full_bar[stage], 0, x0 + STEM_BW * half, y0, b);
+          if (p.debug & 4) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], STEM_BOX_BYTES);
+            tma_load_4d(smem_a + stage * STEM_STAGE_BYTES, &tmap_a, &full_bar[stage], 0, x0 + STEM_BW * half, y0, b);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -154,7 +168,7 @@ stem_s2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t a0 = smem_u32(smem_a + stage * STEM_STAGE_BYTES);
         if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < STEM_TAPS; ++tap) {
+          for (int tap = 0; tap < ((p.debug & 2) ? 1 : STEM_TAPS); ++tap) {
             const uint64_t da = make_smem_desc32(a0 + (uint32_t)(((tap >> 2) * STEM_HW + (tap & 3)) * STEM_ROW_BYTES), STEM_HW * STEM_ROW_BYTES);
             const uint64_t db = make_smem_desc32(w0 + (uint32_t)(tap * STEM_TAP_BYTES), 8 * STEM_ROW_BYTES);
             umma_bf16(tmem_d, da, db, idesc, tap != 0 ? 1u : 0u);
@@ -193,14 +207,19 @@ stem_s2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[set]);   // both halves are in registers: the MMA warp may refill the slot
         }
+        if (p.debug & 1) continue;
         const int xl = STEM_BW * half + xx;
         const int x = tx * Cfg::kStep + Cfg::kOrigin + xl;
         const bool valid = y >= 0 && y < p.Hout && x >= 0 && x < p.Wout;
+        // relu(acc + bias) -> bf16: one packed FFMA2 (x * 1 + b is the exact sum) and one converting instruction with the
+        // ReLU folded in per channel pair
         uint32_t w[32];
+        const uint64_t one2 = pk2(1.f, 1.f);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float2 bb = *reinterpret_cast<const float2*>(s_bias + 2 * j);
-          w[j] = bf16x2_rn(fmaxf(__uint_as_float(v[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bb.y, 0.f));
+        for (int j = 0; j < 16; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + 4 * j);
+          w[2 * j] = relu_bf16x2_rn(fma2(pk2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), one2, pk2(bb.x, bb.y)));
+          w[2 * j + 1] = relu_bf16x2_rn(fma2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), one2, pk2(bb.z, bb.w)));
         }
         if (POOL) {
           const int pl = yy * 16 + xl;
@@ -216,7 +235,7 @@ stem_s2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int c = 0; c < 8; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         }
       }
-      if (POOL) {
+      if (POOL && !(p.debug & 1)) {
         named_bar_sync(1 + set, 128);
         for (int wi = et; wi < 49 * 8; wi += 128) {
           const int pp = wi >> 3, c = wi & 7;
@@ -293,6 +312,8 @@ int launch_stem_cfg(const __nv_bfloat16* x, const __nv_bfloat16* w_taps, const f
   p.num_tiles = (int)total;
   p.bias = bias;
   p.out = out;
+  static const int debug = [] { const char* e = getenv("SX_STEM_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = debug;
   auto kern = stem_s2d_tc_kernel<STAGES, SETS, POOL>;
   const size_t smem = Cfg::smem_bytes();
   static bool configured = false;  // per instantiation
@@ -310,7 +331,14 @@ int launch_stem_cfg(const __nv_bfloat16* x, const __nv_bfloat16* w_taps, const f
 // bias: fp32 [64]; out: NHWC bf16 [B, Hin-3, Win-3, 64], or with fuse_pool the 3x3/2/1 max-pooled map of it.
 inline int launch_stem_s2d(const __nv_bfloat16* x, const __nv_bfloat16* w_taps, const float* bias, __nv_bfloat16* out, int B, int Hin,
                            int Win, int fuse_pool, cudaStream_t stream) {
-  if (fuse_pool) return launch_stem_cfg<8, 2, true>(x, w_taps, bias, out, B, Hin, Win, stream);
+  static const int variant = [] { const char* e = getenv("SX_STEM_VARIANT"); return e ? atoi(e) : 0; }();
+  if (fuse_pool) {
+    // measured alone at B = 256 (profiles/exp_stem.py, r03): 2 epilogue sets 0.187 ms, 3 sets 0.162 ms; the MMAs alone
+    // (SX_STEM_DEBUG=5) take 0.143 ms -- K = 16 per instruction is paced by the 6 KB of operands it reads from shared memory
+    if (variant == 1) return launch_stem_cfg<8, 2, true>(x, w_taps, bias, out, B, Hin, Win, stream);
+    if (variant == 2) return launch_stem_cfg<6, 4, true>(x, w_taps, bias, out, B, Hin, Win, stream);
+    return launch_stem_cfg<8, 3, true>(x, w_taps, bias, out, B, Hin, Win, stream);
+  }
   return launch_stem_cfg<8, 3, false>(x, w_taps, bias, out, B, Hin, Win, stream);
 }
 
