@@ -71,7 +71,8 @@ def parse():
                     help="classifier input pipeline: one native kernel or torchvision resize + Normalize")
     ap.add_argument("--latents-per-step", type=int, default=1)
     ap.add_argument("--pool", type=int, default=16, help="latents per rank prepared up front (minima/maxima pool)")
-    ap.add_argument("--max-batch", type=int, default=256)
+    ap.add_argument("--max-batch", type=int, default=None,
+                    help="perturbed images per launch; default attfind.default_eval_batch(image size): 256 at 256 px, 1024 at 64 px")
     ap.add_argument("--cpu-sample-coords", type=int, default=60, help="style coordinates in the CPU-baseline sample")
     ap.add_argument("--cpu-sample-images", type=int, default=2, help="images in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -378,6 +379,8 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False          # fp32 work (calibration, the parity-mode verification) is real fp32;
     torch.backends.cuda.matmul.allow_tf32 = False    # the bf16 throughput classifier is not affected
     size, kind = args.image_size, args.classifier
+    if args.max_batch is None:
+        args.max_batch = sx.attfind.default_eval_batch(size)
     if args.classifier_dtype is None:
         args.classifier_dtype = "bf16" if kind == "resnet" else "fp32"
     sd, model_cpu, noise_cpu = build_workload(size, kind)
@@ -583,7 +586,7 @@ def run_ours(args):
         "config": {"workload": workload_name(size, S, kind) + f", {lps} latent(s)/rank/step x {S} coords x 2 directions",
                    "coord_evals_per_step": int(2 * S * lps * world), "max_batch": args.max_batch,
                    "generator_dtype": args.precision, "classifier_dtype": info.get("dtype", args.classifier_dtype) + " (PyTorch, channels_last)", "classifier_mode": clf_mode, "classifier_preprocess": pre_mode,
-                   "prefix_reuse": True, "l2": f"inputs larger than L2: every {args.max_batch}-eval batch streams >{args.max_batch * 16.8e6 / 1e9:.1f} GB of activations (L2 = 126 MB)",
+                   "prefix_reuse": True, "l2": f"inputs larger than L2: every {args.max_batch}-eval batch streams >{args.max_batch * 16.8e6 * (size / 256) ** 2 / 1e9:.1f} GB of activations (L2 = 126 MB)",
                    "pool_latents": pool_n, "parallelism": f"latent-sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot[1].item()), "roofline": roofline, "cpu_baseline": cpu,
         "job": job, "conv_flops_per_full_image": conv_flops_per_image(plan.pairs),

@@ -80,9 +80,17 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def default_eval_batch(image_size: int) -> int:
+    """Perturbed images per generator / classifier launch when the caller does not say.  The notebook evaluates ONE per
+    forward (NB:383); the batch only changes how many loop iterations share a launch, never a value.  256 at 256 px (the
+    32-bit element indices of the narrow-layer kernels end at batch 511 there); small maps want more rows per launch --
+    measured at 64 px with ResNet-18@224: 140.1 k coord-evals/s at 256, 146.6 k at 512, 155.9 k at 1024."""
+    return 256 if image_size >= 256 else 512 if image_size >= 128 else 1024
+
+
 @torch.no_grad()
 def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.Tensor, shift_size: float = 1.0,
-                  precision: Optional[str] = None, max_batch: int = 128, rank: int = 0, world_size: int = 1,
+                  precision: Optional[str] = None, max_batch: Optional[int] = None, rank: int = 0, world_size: int = 1,
                   sindices: Optional[Sequence[int]] = None, image_indices: Optional[Sequence[int]] = None,
                   gather: bool = True, stats: Optional[dict] = None,
                   minmax: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
@@ -111,6 +119,7 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     L = G.num_layers
     S, row = plan.S, plan.row
     n_all = latents.shape[0]
+    max_batch = default_eval_batch(G.image_size) if max_batch is None else max_batch
     max_batch = max(2, max_batch - (max_batch % 2))
     half = max_batch // 2
     plan.reserve(max_batch, precision)
@@ -533,7 +542,7 @@ DATASET_NAMES = ("style_change", "latents", "base_prob", "minima", "maxima", "st
 @torch.no_grad()
 def attfind_extraction(dataloader, num_images, results_folder, stylex, classifier, dataset_name, noise, num_style_coords,
                        shift_size, discriminator_threshold, image_size=64, batch_size=1, cuda_rank=0,
-                       use_discriminator=False, use_old_architecture=True, precision=None, max_batch=128,
+                       use_discriminator=False, use_old_architecture=True, precision=None, max_batch=None,
                        rank=0, world_size=1, front_batch=256, verify_classifier=None, num_indices=5, effect_threshold=0.5):
     """``attfind_extraction`` of NB:269-417 with the same arguments (extra keyword arguments have defaults).
 
@@ -610,7 +619,8 @@ def _attfind_extraction(dataloader, num_images, results_folder, stylex, classifi
     if verify_classifier is not None:
         picks, merged, scores, info = attfind_verify_topk(G, verify_classifier, image_latents[:images_found], noise, res,
                                                           num_indices, effect_threshold, shift_size=shift_size, precision="fp32",
-                                                          max_batch=max_batch, rank=rank, world_size=world_size)
+                                                          max_batch=128 if max_batch is None else min(max_batch, 256),
+                                                          rank=rank, world_size=world_size)
         res = dict(res, style_change=info["style_change"], base_prob=info["base_prob"])
         extra = {"picks": picks, "merged": merged, "verify": {k: v for k, v in info.items() if k not in ("style_change", "base_prob")}}
     out = {
