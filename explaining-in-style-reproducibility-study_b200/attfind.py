@@ -88,13 +88,18 @@ def default_eval_batch(image_size: int) -> int:
     return 256 if image_size >= 256 else 512 if image_size >= 128 else 1024
 
 
+def default_classify_batch() -> int:
+    """Images per classifier call of the sweep (the outputs of several generator launches)."""
+    return int(os.environ.get("SX_CLASSIFY_BATCH", 1024))
+
+
 @torch.no_grad()
 def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.Tensor, shift_size: float = 1.0,
                   precision: Optional[str] = None, max_batch: Optional[int] = None, rank: int = 0, world_size: int = 1,
                   sindices: Optional[Sequence[int]] = None, image_indices: Optional[Sequence[int]] = None,
                   gather: bool = True, stats: Optional[dict] = None,
                   minmax: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                  zero_row: bool = False) -> Dict[str, torch.Tensor]:
+                  zero_row: bool = False, classify_batch: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Phases A(second half)-C of ``attfind_extraction`` (NB:316-389) for latents ``[N, latent]``.
 
     Every rank computes the style coordinates, base images and base logits of ALL N latents (cheap, and it
@@ -109,6 +114,7 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     NB:340); by default they are computed from ``latents``.  ``zero_row``: an all-zero style row takes part in the
     extrema -- what the notebook computes when fewer images pass the discriminator filter than ``num_images`` (its
     ``style_coordinates`` buffer keeps zero rows for the images it never found, and NB:340 reduces over the whole buffer).
+    ``classify_batch``: images per classifier call (>= ``max_batch``; default ``default_classify_batch()``).
     """
     precision = precision or G.precision
     N.require_cuda(latents, noise)
@@ -155,20 +161,36 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     runs = _coord_runs(plan.conv_coords, sindices, half)
     # per-plan scratch, kept across calls (bench.py sweeps one latent per call: 201 MB of rgb at batch 256 / 256 px)
     styles_b = plan.scratch("sweep_styles", (max_batch, row), dev)
-    rgb_b = plan.scratch("sweep_rgb", (max_batch, 3, G.image_size, G.image_size), dev)
+    # the classifier takes the images of several generator launches at once (its small-map layers want more rows than the
+    # generator's index range allows per launch at 256 px): generator batches fill slices of one image buffer
+    cb = max(max_batch, default_classify_batch() if classify_batch is None else int(classify_batch))
+    rgb_b = plan.scratch("sweep_rgb", (cb, 3, G.image_size, G.image_size), dev)
     evals = 0
     for n in mine:                                                                      # NB:346
         base_row = styles_all[n]
         plan.forward(styles_all[n: n + 1], noise, save_cache=True, precision=precision, out=rgb_b[:1])
+        pending, fill = [], 0
+
+        def flush():
+            logits = classifier.classify_images(rgb_b[:fill]).float().contiguous()      # NB:384 (raw rgb, quirk Q4)
+            for off, first, cnt in pending:
+                N.check(lib.sx_attfind_scatter_effects(logits.data_ptr() + off * logits.stride(0) * 4, base_logits[n].data_ptr(),
+                                                       effects[n - lo].data_ptr(), 0, S, first, cnt, stream),
+                        "sx_attfind_scatter_effects")
+
         for conv, first, cnt in runs:                                                   # NB:356-387, batched per conv
             b = 2 * cnt
+            if fill + b > cb:
+                flush()
+                pending, fill = [], 0
             N.check(lib.sx_attfind_make_styles(base_row.data_ptr(), minima.data_ptr(), maxima.data_ptr(), styles_b.data_ptr(),
                                                row, first, cnt, float(shift_size), stream), "sx_attfind_make_styles")
-            rgb = plan.forward(styles_b[:b], noise, start_conv=conv, precision=precision, out=rgb_b[:b])
-            logits = classifier.classify_images(rgb).float().contiguous()               # NB:384 (raw rgb, quirk Q4)
-            N.check(lib.sx_attfind_scatter_effects(logits.data_ptr(), base_logits[n].data_ptr(), effects[n - lo].data_ptr(),
-                                                   0, S, first, cnt, stream), "sx_attfind_scatter_effects")
+            plan.forward(styles_b[:b], noise, start_conv=conv, precision=precision, out=rgb_b[fill: fill + b])
+            pending.append((fill, first, cnt))
+            fill += b
             evals += b
+        if fill:
+            flush()
     if stats is not None:
         stats["coord_evals"] = stats.get("coord_evals", 0) + evals
     if gather and world_size > 1:

@@ -1231,6 +1231,11 @@ def test_sweep_edge_cases(dev, tc_ok, precision):
     b = sx.attfind_sweep(G, clf, lat, noise, precision=precision, sindices=sind, max_batch=4096)   # one batch per conv
     # our kernels are batch-size independent; the tiny classifier is one cuDNN conv whose algorithm may not be
     assert float((a["style_change"] - b["style_change"]).abs().max()) <= 1e-4
+    # images per classifier call: one generator launch each, or several launches gathered (flush in the middle of a latent)
+    c = sx.attfind_sweep(G, clf, lat, noise, precision=precision, sindices=sind, max_batch=8, classify_batch=8)
+    d = sx.attfind_sweep(G, clf, lat, noise, precision=precision, sindices=sind, max_batch=8, classify_batch=20)
+    assert float((c["style_change"] - a["style_change"]).abs().max()) <= 1e-4
+    assert float((d["style_change"] - a["style_change"]).abs().max()) <= 1e-4
     mask = torch.ones(S, dtype=torch.bool)
     mask[sind] = False
     assert float(a["style_change"][:, :, mask].abs().max()) == 0.0
