@@ -636,3 +636,38 @@ def test_configure_throughput_rejects_a_reduced_precision_network_that_moves_the
     net2 = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(192, 2)).eval()
     c2 = sx.MobileNet(model=net2, image_size=8, normalize=False)
     assert c2.configure_throughput(probe, dtype=torch.bfloat16)["dtype"] == "bfloat16"
+
+
+def test_launch_batch_defaults_and_native_stem_host_checks(monkeypatch):
+    """the per-launch batch defaults (host logic), the stem weights' tap layout, and that the native stem refuses to be
+    enabled where it cannot run (CPU weights / a non-bf16 network / before the space-to-depth re-expression)."""
+    from stylex_b200.classifiers import FusedResNetInference, space_to_depth_input, stem_weight_to_s2d
+    assert [attfind.default_eval_batch(s) for s in (16, 64, 128, 256, 1024)] == [1024, 1024, 512, 256, 256]
+    monkeypatch.delenv("SX_CLASSIFY_BATCH", raising=False)
+    assert attfind.default_classify_batch() == 1024
+    monkeypatch.setenv("SX_CLASSIFY_BATCH", "256")
+    assert attfind.default_classify_batch() == 256
+    # 7x7 / stride 2 / pad 3 on the image == 4x4 / stride 1 / pad 0 on the space-to-depth image (what the stem kernel computes),
+    # and the kernel's tap-major weight layout [ky][kx][co][ci] is a pure re-indexing of those weights
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(64, 3, 7, 7, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 3, 20, 24, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv2d(x, w, stride=2, padding=3)
+    w2 = stem_weight_to_s2d(w)
+    got = torch.nn.functional.conv2d(space_to_depth_input(x), w2)
+    assert got.shape == ref.shape and float((got - ref).abs().max()) < 1e-12
+    taps = w2.permute(2, 3, 0, 1).contiguous()
+    xs = space_to_depth_input(x)
+    manual = sum(torch.einsum("bchw,oc->bohw", xs[:, :, ky: ky + ref.shape[2], kx: kx + ref.shape[3]], taps[ky, kx])
+                 for ky in range(4) for kx in range(4))
+    assert float((manual - ref).abs().max()) < 1e-12
+    f = FusedResNetInference.__new__(FusedResNetInference)
+    f.dtype, f.stem_s2d, f.native_stem = torch.bfloat16, None, None
+    with pytest.raises(RuntimeError, match="enable_s2d_stem"):
+        f.enable_native_stem()
+    f.stem_s2d = (w2.to(torch.bfloat16), torch.zeros(64, dtype=torch.bfloat16))          # CPU weights
+    with pytest.raises(TypeError, match="bf16 CUDA weights"):
+        f.enable_native_stem()
+    f.dtype = torch.float32
+    with pytest.raises(TypeError):
+        f.enable_native_stem()
