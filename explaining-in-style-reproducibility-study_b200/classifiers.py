@@ -239,6 +239,7 @@ class FusedResNetInference:
         self.stem_s2d = None
         self.native_pool = False
         self.native_stem = None
+        self.gemm_shortcut = True
 
     def enable_native_stem(self, fuse_pool: bool = True):
         """Opt-in (bf16, 64 stem channels, after ``enable_s2d_stem``): conv1 + bn1 + relu -- and with ``fuse_pool`` the
@@ -323,11 +324,25 @@ class FusedResNetInference:
         w = (w * scale[:, None, None, None]).to(self.dtype).contiguous(memory_format=torch.channels_last)
         return w, b.to(self.dtype), tuple(conv.stride), tuple(conv.padding)
 
+    def _shortcut(self, x: torch.Tensor, ds) -> torch.Tensor:
+        """The 1x1 strided shortcut convolution + its (BatchNorm) bias.  ``F.conv2d`` runs cuDNN's convolution and then a
+        separate elementwise pass for the bias (7 % of the 64 px AttFind step); as a GEMM over the gathered pixels the bias
+        is part of the cuBLASLt epilogue (added in fp32 before the one rounding), and the gather moves half the bytes the
+        bias pass did."""
+        w, b, stride, padding = ds
+        if not (self.gemm_shortcut and x.is_cuda and tuple(w.shape[2:]) == (1, 1) and padding == (0, 0)):
+            return F.conv2d(x, w, b, stride, padding)
+        xs = x[:, :, ::stride[0], ::stride[1]]
+        n, c, h, wd = xs.shape
+        rows = xs.permute(0, 2, 3, 1).reshape(n * h * wd, c)                         # the gather (one copy)
+        out = F.linear(rows, w.reshape(w.shape[0], c), b)
+        return out.view(n, h, wd, w.shape[0]).permute(0, 3, 1, 2)                     # channels_last [n, Co, h, wd]
+
     def _trunk(self, x: torch.Tensor, pooled: bool = False) -> torch.Tensor:
         if not pooled:
             x = self._pool(x)
         for (w1, b1, s1, p1), (w2, b2, s2, p2), ds in self.blocks:
-            identity = x if ds is None else F.conv2d(x, ds[0], ds[1], ds[2], ds[3])
+            identity = x if ds is None else self._shortcut(x, ds)
             out = torch.cudnn_convolution_relu(x, w1, b1, s1, p1, (1, 1), 1)
             x = torch.cudnn_convolution_add_relu(out, w2, identity, 1.0, b2, s2, p2, (1, 1), 1)
         x = x.mean((2, 3))
