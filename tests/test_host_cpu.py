@@ -671,3 +671,40 @@ def test_launch_batch_defaults_and_native_stem_host_checks(monkeypatch):
     f.dtype = torch.float32
     with pytest.raises(TypeError):
         f.enable_native_stem()
+
+
+def test_fused_resnet_shortcut_as_gemm_equals_the_convolution():
+    """FusedResNetInference (CPU, fp32): folded BatchNorm + the 1x1 strided shortcut convolutions as gather + GEMM with the
+    bias in the epilogue give the eager module's logits; switching the GEMM form off changes nothing beyond rounding."""
+    from stylex_b200.classifiers import FusedResNetInference
+    model = synthetic.make_classifier_model("resnet", 3).eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    with torch.no_grad():
+        ref = model(x)
+        f = FusedResNetInference.__new__(FusedResNetInference)
+        f.dtype = torch.float32
+        f.stem = f._fold(model.conv1, model.bn1)
+        f.blocks = [(f._fold(b.conv1, b.bn1), f._fold(b.conv2, b.bn2),
+                     None if b.downsample is None else f._fold(b.downsample[0], b.downsample[1]))
+                    for layer in (model.layer1, model.layer2, model.layer3, model.layer4) for b in layer]
+        f.fc_w, f.fc_b = model.fc.weight.detach(), model.fc.bias.detach()
+        f.stem_s2d, f.native_pool, f.native_stem, f.gemm_shortcut = None, False, None, True
+        assert sum(ds is not None for _, _, ds in f.blocks) == 3
+        w, b, s, p = f.stem
+        h = torch.relu(torch.nn.functional.conv2d(x, w, b, s, p))       # cudnn_convolution_relu's arithmetic, on the CPU
+
+        def trunk(f, h):
+            h = torch.nn.functional.max_pool2d(h, 3, 2, 1)
+            for (w1, b1, s1, p1), (w2, b2, s2, p2), ds in f.blocks:
+                idn = h if ds is None else f._shortcut(h, ds)
+                o = torch.relu(torch.nn.functional.conv2d(h, w1, b1, s1, p1))
+                h = torch.relu(torch.nn.functional.conv2d(o, w2, b2, s2, p2) + idn)
+            return torch.nn.functional.linear(h.mean((2, 3)), f.fc_w, f.fc_b)
+
+        got = trunk(f, h)
+        f.gemm_shortcut = False
+        plain = trunk(f, h)
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= 2e-4 * scale
+    assert float((got - plain).abs().max()) <= 1e-5 * scale
