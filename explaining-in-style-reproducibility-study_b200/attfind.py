@@ -88,9 +88,13 @@ def default_eval_batch(image_size: int) -> int:
     return 256 if image_size >= 256 else 512 if image_size >= 128 else 1024
 
 
-def default_classify_batch() -> int:
-    """Images per classifier call of the sweep (the outputs of several generator launches)."""
-    return int(os.environ.get("SX_CLASSIFY_BATCH", 1024))
+def default_classify_batch(image_size: int = 256) -> int:
+    """Images per classifier call of the sweep (the outputs of several generator launches): 1024 while the fp32 image
+    buffer stays within 1 GiB (up to 256 px); measured at 256 px: 256 -> 1024 +2.3 %, 2048 nothing more."""
+    env = os.environ.get("SX_CLASSIFY_BATCH")
+    if env:
+        return int(env)
+    return max(1, min(1024, (1 << 30) // (12 * image_size * image_size)))
 
 
 @torch.no_grad()
@@ -163,7 +167,7 @@ def attfind_sweep(G: Generator, classifier, latents: torch.Tensor, noise: torch.
     styles_b = plan.scratch("sweep_styles", (max_batch, row), dev)
     # the classifier takes the images of several generator launches at once (its small-map layers want more rows than the
     # generator's index range allows per launch at 256 px): generator batches fill slices of one image buffer
-    cb = max(max_batch, default_classify_batch() if classify_batch is None else int(classify_batch))
+    cb = max(max_batch, default_classify_batch(G.image_size) if classify_batch is None else int(classify_batch))
     rgb_b = plan.scratch("sweep_rgb", (cb, 3, G.image_size, G.image_size), dev)
     evals = 0
     for n in mine:                                                                      # NB:346

@@ -644,9 +644,9 @@ def test_launch_batch_defaults_and_native_stem_host_checks(monkeypatch):
     from stylex_b200.classifiers import FusedResNetInference, space_to_depth_input, stem_weight_to_s2d
     assert [attfind.default_eval_batch(s) for s in (16, 64, 128, 256, 1024)] == [1024, 1024, 512, 256, 256]
     monkeypatch.delenv("SX_CLASSIFY_BATCH", raising=False)
-    assert attfind.default_classify_batch() == 1024
+    assert [attfind.default_classify_batch(s) for s in (64, 256, 512, 1024)] == [1024, 1024, 341, 85]
     monkeypatch.setenv("SX_CLASSIFY_BATCH", "256")
-    assert attfind.default_classify_batch() == 256
+    assert attfind.default_classify_batch(64) == 256
     # 7x7 / stride 2 / pad 3 on the image == 4x4 / stride 1 / pad 0 on the space-to-depth image (what the stem kernel computes),
     # and the kernel's tap-major weight layout [ky][kx][co][ci] is a pure re-indexing of those weights
     g = torch.Generator().manual_seed(3)
